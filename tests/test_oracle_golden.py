@@ -1,0 +1,188 @@
+"""Pins the CPU oracle (oracle/mp_oracle.c) against golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py) and the reference's own known-answer tests."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, load_golden
+from oracle import oracle as O
+
+
+@pytest.mark.parametrize("F", [1, 5])
+@pytest.mark.parametrize("red", ["sum", "mean", "min", "max", "mul"])
+def test_scatter(F, red):
+    g = load_golden(f"scatter_F{F}")
+    N = int(g["N"])
+    out = O.scatter(g["src"], g["index"], N, red)
+    assert_close(out, g["out_" + red], msg=red)
+    if red != "mul":
+        gs = O.scatter_backward(g["gout_" + red], g["src"], out, g["index"], red)
+        assert_close(gs, g["gsrc_" + red], msg="bwd " + red)
+
+
+def test_scatter_max_ties_split_evenly():
+    # ATen scatter_reduce backward splits evenly among tied maxima.
+    src = np.array([[1., -2.], [1., -3.]], np.float32)
+    index = np.array([0, 0])
+    out = O.scatter(src, index, 1, "max")
+    gs = O.scatter_backward(np.ones((1, 2), np.float32), src, out, index, "max")
+    assert_close(gs, [[0.5, 1.0], [0.5, 0.0]])
+
+
+@pytest.mark.parametrize("red", ["sum", "mean", "min", "max"])
+def test_segment(red):
+    g = load_golden("segment")
+    assert_close(O.segment(g["src"], g["ptr"], red), g["out_" + red], msg=red)
+
+
+def test_segment_matches_dense_reductions():
+    # test/utils/test_segment.py:13-31: empty first segment -> 0
+    rng = np.random.default_rng(0)
+    src = rng.standard_normal((20, 16)).astype(np.float32)
+    ptr = np.array([0, 0, 5, 10, 15, 20])
+    out = O.segment(src, ptr, "sum")
+    assert_close(out[0], np.zeros(16))
+    assert_close(out[1:], src.reshape(4, 5, 16).sum(1), rtol=1e-5, atol=1e-5)
+    assert_close(O.segment(src, ptr, "max")[1:], src.reshape(4, 5, 16).max(1))
+    assert_close(O.segment(src, ptr, "min")[0], np.zeros(16))
+
+
+def test_softmax():
+    g = load_golden("softmax")
+    assert_close(O.softmax(g["src1"], g["index1"], 3), [0.5, 0.5, 1, 1])  # test_softmax.py:12-27
+    assert_close(O.softmax(g["src1"], g["index1"], 3), g["out1_ptr"])
+    N = int(g["N"])
+    out = O.softmax(g["src"], g["index"], N)
+    assert_close(out, g["out"])
+    assert_close(out, g["out_ptr"])
+    assert_close(O.softmax_backward(g["gout"], out, g["index"], N), g["gsrc"], rtol=1e-4, atol=1e-6)
+
+
+def test_structure():
+    g = load_golden("structure")
+    assert np.array_equal(O.degree(g["deg_index"], 3), [3, 1, 1])  # test/utils/test_degree.py
+    assert np.array_equal(O.degree(g["deg_index"], 3), g["deg"])
+    assert np.array_equal(O.index2ptr(g["idx_sorted"], 11), g["ptr"])
+    assert np.array_equal(O.ptr2index(g["ptr"]), g["ptr2idx"])
+    perm, ptr = O.stable_sort_by_key(g["ei"][1], 11)
+    assert np.array_equal(perm, g["stable_perm"])
+    assert np.array_equal(ptr, g["ptr"])
+    # test/utils/test_loop.py:220-291 shape of the answer; SURVEY section 9 exact values
+    r, c, w = O.add_remaining_self_loops(g["row"], g["col"], g["w"], 3, 1.0)
+    assert np.array_equal(np.stack([r, c]), g["asl_ei"])
+    assert np.array_equal(np.stack([r, c]), [[0, 1, 2, 0, 1, 2], [1, 0, 1, 0, 1, 2]])
+    assert_close(w, g["asl_w"])
+    assert_close(w, [3, 4, 6, 2, 1, 5])
+    r, c, _ = O.add_remaining_self_loops(g["row"], g["col"], None, 3)
+    assert np.array_equal(np.stack([r, c]), g["asl_ei_now"])
+    r, c, w = O.add_remaining_self_loops(g["ei"][0], g["ei"][1], g["wr"], 11, 2.0)
+    assert np.array_equal(np.stack([r, c]), g["asl_eiR"])
+    assert_close(w, g["asl_wR"])
+
+
+@pytest.mark.parametrize("tag,use_w,improved,asl", [("a", False, False, True), ("b", True, False, True),
+                                                     ("c", True, True, True), ("d", True, False, False)])
+def test_gcn_norm(tag, use_w, improved, asl):
+    g = load_golden("gcn_norm")
+    r, c, w = O.gcn_norm(g["ei"][0], g["ei"][1], g["wr"] if use_w else None, int(g["N"]), improved, asl)
+    assert np.array_equal(np.stack([r, c]), g["ei_" + tag])
+    assert_close(w, g["w_" + tag], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("red", ["sum", "mean", "min", "max"])
+def test_spmm_and_matmul(red):
+    g = load_golden("spmm")
+    N = int(g["N"])
+    ei, x = g["ei_sorted"], g["x"]
+    # EdgeIndex.matmul: out[row] = reduce over col of x[col]  (edge_index.py:1903-1922)
+    out = O.gather_scatter(x, ei[1], ei[0], None, N, red)
+    assert_close(out, g["out_" + red], msg=red)
+    ptr = O.index2ptr(ei[0], N)
+    assert_close(O.spmm_csr(ptr, ei[1], None, x, red), g["out_" + red], msg="csr " + red)
+    gx, _ = O.gather_scatter_backward(g["gout_" + red], x, out, ei[1], ei[0], None, red)
+    assert_close(gx, g["gx_" + red], rtol=1e-5, atol=1e-6, msg="gx " + red)
+
+
+def test_spmm_weighted():
+    g = load_golden("spmm")
+    N = int(g["N"])
+    ei, x, val = g["ei_sorted"], g["x"], g["val_sorted"]
+    out = O.gather_scatter(x, ei[1], ei[0], val, N, "sum")
+    assert_close(out, g["out_wsum"])
+    ptr = O.index2ptr(ei[0], N)
+    assert_close(O.spmm_csr(ptr, ei[1], val, x, "sum"), g["out_spmm_wsum"])
+    assert_close(O.spmm_csr(ptr, ei[1], val, x, "mean"), g["out_spmm_wmean"])
+    gx, gw = O.gather_scatter_backward(g["gout_wsum"], x, out, ei[1], ei[0], val, "sum", True)
+    assert_close(gx, g["gx_wsum"], rtol=1e-5, atol=1e-6)
+    assert_close(gw, g["gval_wsum"], rtol=1e-5, atol=1e-6)
+
+
+def test_aggr_modules():
+    g = load_golden("aggr")
+    N = int(g["N"])
+    for red in ("sum", "mean", "max", "min"):
+        assert_close(O.scatter(g["x"], g["index"], N, red), g["out_" + red], msg=red)
+        assert_close(O.segment(g["x"], g["ptr"], red), g["out_" + red], msg="ptr " + red)
+    # SoftmaxAggregation (aggr/basic.py:196-215): alpha = softmax(x*t); out = sum(x*alpha)
+    alpha = O.softmax(g["x"], g["index"], N)
+    assert_close(O.scatter(g["x"] * alpha, g["index"], N, "sum"), g["out_softmax"])
+
+
+def test_gcn_conv_cora_two_layers():
+    g = load_golden("gcn_cora")
+    ei, x = g["ei"], g["x"]
+    h1 = O.gcn_conv(x, ei[0], ei[1], None, g["w1"], g["b1"])
+    assert_close(h1, g["h1"], rtol=1e-4, atol=1e-5)
+    a1 = np.maximum(h1, 0)
+    out = O.gcn_conv(a1, ei[0], ei[1], None, g["w2"], g["b2"])
+    assert_close(out, g["out"], rtol=1e-4, atol=1e-5)
+    ga1, gw2, gb2 = O.gcn_conv_backward(g["gout"], a1, ei[0], ei[1], None, g["w2"])
+    assert_close(gw2, g["gw2"], rtol=1e-4, atol=1e-4)
+    assert_close(gb2, g["gb2"], rtol=1e-4, atol=1e-4)
+    gh1 = ga1 * (h1 > 0)
+    gx, gw1, gb1 = O.gcn_conv_backward(gh1, x, ei[0], ei[1], None, g["w1"])
+    assert_close(gx, g["gx"], rtol=1e-4, atol=1e-5)
+    assert_close(gw1, g["gw1"], rtol=1e-4, atol=1e-4)
+    assert_close(gb1, g["gb1"], rtol=1e-4, atol=1e-4)
+
+
+def test_gcn_conv_weighted_improved():
+    g = load_golden("gcn_small")
+    ei = g["ei"]
+    out = O.gcn_conv(g["x"], ei[0], ei[1], g["w"], g["weight"], g["bias"], improved=True)
+    assert_close(out, g["out"], rtol=1e-5, atol=1e-6)
+    gx, gw, gb = O.gcn_conv_backward(g["gout"], g["x"], ei[0], ei[1], g["w"], g["weight"], improved=True)
+    assert_close(gx, g["gx"], rtol=1e-5, atol=1e-6)
+    assert_close(gw, g["gweight"], rtol=1e-5, atol=1e-5)
+    assert_close(gb, g["gbias"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("aggr", ["mean", "max", "sum"])
+def test_sage_conv(aggr):
+    g = load_golden("sage_gin")
+    ei = g["ei"]
+    out = O.sage_conv(g["x"], ei[0], ei[1], g["wl_" + aggr], g["bl_" + aggr], g["wr_" + aggr], aggr)
+    assert_close(out, g["out_" + aggr], rtol=1e-5, atol=1e-6)
+
+
+def test_gin_aggregate():
+    g = load_golden("sage_gin")
+    assert_close(O.gin_aggregate(g["x"], g["ei"][0], g["ei"][1], 0.25), g["gin_out"], rtol=1e-5, atol=1e-6)
+
+
+def test_gat_attention():
+    g = load_golden("gat")
+    H, C = 4, 3
+    xh = O.linear(g["x"], g["lin"]).reshape(-1, H, C)
+    out, alpha, r2, c2 = O.gat_attention(xh, g["att_src"].reshape(H, C), g["att_dst"].reshape(H, C),
+                                         g["ei"][0], g["ei"][1], float(g["slope"]))
+    assert np.array_equal(np.stack([r2, c2]), g["ei2"])  # test_gat_conv.py:55-58 edge order
+    assert_close(alpha, g["alpha"], rtol=1e-5, atol=1e-6)
+    assert_close(out + g["bias"], g["out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("aggr", ["mean", "sum"])
+def test_rgcn_conv(aggr):
+    g = load_golden("rgcn")
+    out = O.rgcn_conv(g["x"], g["ei"][0], g["ei"][1], g["et"], g["weight_" + aggr], g["root_" + aggr],
+                      g["bias_" + aggr], aggr)
+    assert_close(out, g["out_" + aggr], rtol=1e-5, atol=1e-6)
