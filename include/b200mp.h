@@ -1,0 +1,222 @@
+/*
+ * b200mp.h -- C ABI of the B200-native message-passing aggregation engine.
+ *
+ * This is the drop-in boundary.  The reference
+ * (pyg-team/pytorch_geometric v2.9.0) has no FFI of its own: it late-binds a small set of
+ * operator signatures (torch_scatter.*, torch.ops.torch_sparse.spmm_*, pyg_lib.ops.*) and a few
+ * Python functions.  Each entry point below states which of those it replaces (file:line under
+ * /root/reference/torch_geometric).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes; no torch types.  All pointers are DEVICE pointers unless the
+ *    name ends in _host.  Buffers are caller-owned; nothing is allocated inside.
+ *  - feature matrices are row-major, contiguous, [rows, feat]; `val_dtype` selects the element
+ *    type (B200MP_F32 / B200MP_BF16); accumulation is always fp32.
+ *  - index arrays (`rowptr`, `col`, `index`, `perm`) share one `idx_dtype` per call
+ *    (B200MP_I32 / B200MP_I64).  The reference uses int64; int32 halves index traffic and is
+ *    what the engine's own graph cache stores when N, E < 2^31.
+ *  - edge weights / attention values are always fp32.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *    enqueue work; they never synchronise unless documented.
+ *  - return value: 0 on success, a negative B200MP_ERR_* code otherwise.  Nothing throws
+ *    across the ABI.  A kernel cannot raise: out-of-range indices are undefined behaviour
+ *    unless b200mp_validate_index() is called first (the reference's "valid indices" IndexError,
+ *    nn/conv/message_passing.py:269-290, is produced by the host-side mirror from that result).
+ */
+#ifndef B200MP_H_
+#define B200MP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MP_VERSION "0.1.0"
+
+/* element / index dtypes */
+enum { B200MP_F32 = 0, B200MP_BF16 = 1 };
+enum { B200MP_I32 = 0, B200MP_I64 = 1 };
+/* reductions (same codes as oracle/mp_oracle.c) */
+enum { B200MP_SUM = 0, B200MP_MEAN = 1, B200MP_MIN = 2, B200MP_MAX = 3, B200MP_MUL = 4 };
+/* errors */
+enum {
+    B200MP_OK = 0,
+    B200MP_ERR_INVALID_ARG = -1,   /* NULL pointer, negative size, misaligned buffer */
+    B200MP_ERR_UNSUPPORTED = -2,   /* dtype / reduce combination not implemented */
+    B200MP_ERR_CUDA = -3,          /* a CUDA API call or launch failed; see b200mp_last_error() */
+    B200MP_ERR_WORKSPACE = -4      /* workspace too small */
+};
+
+const char* b200mp_version(void);
+const char* b200mp_last_error(void);          /* thread-local, human readable */
+int b200mp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ------------------------------------------------------------------ graph structure (integer work, bit-exact)
+ * Replaces: utils/_degree.py:9-31 (degree), index.py:27-37 (ptr2index / index2ptr ==
+ * torch._convert_indices_from_coo_to_csr / repeat_interleave), utils/_index_sort.py:10-32 and
+ * pyg_lib.ops.index_sort (stable radix sort by key), EdgeIndex.get_csr/get_csc/_sort_by_transpose
+ * (edge_index.py:589-696), utils/loop.py:585-657 (add_remaining_self_loops) and :71-131/:382-492
+ * (remove_self_loops + add_self_loops), nn/conv/gcn_conv.py:95-113 (gcn_norm). */
+
+/* deg[i] = #(index == i); deg has idx_dtype. */
+int b200mp_degree(const void* index, int64_t n_index, int64_t n_nodes, void* deg, int idx_dtype,
+                  void* stream);
+/* ptr[i] = #(index < i) for a SORTED index; ptr has n_nodes + 1 entries. */
+int b200mp_index2ptr(const void* index_sorted, int64_t n_index, int64_t n_nodes, void* ptr,
+                     int idx_dtype, void* stream);
+/* index[e] = i for ptr[i] <= e < ptr[i+1]. */
+int b200mp_ptr2index(const void* ptr, int64_t n_nodes, int64_t n_index, void* index,
+                     int idx_dtype, void* stream);
+/* min / max / sortedness of an index array in one pass: out_host-less, writes 3 int64 to DEVICE
+ * memory stats[3] = {min, max, is_sorted(0/1)} (n_index == 0 -> {0, -1, 1}). */
+int b200mp_index_stats(const void* index, int64_t n_index, int64_t* stats, int idx_dtype,
+                       void* stream);
+/* Stable sort of keys in [0, n_nodes): writes keys_sorted (optional, may be NULL), perm (the
+ * stable argsort, idx_dtype) and ptr (optional, n_nodes+1, the CSR pointer of the sorted keys).
+ * Workspace size from b200mp_sort_workspace_bytes(). */
+int64_t b200mp_sort_workspace_bytes(int64_t n_index, int64_t n_nodes, int idx_dtype);
+int b200mp_sort_by_key(const void* keys, int64_t n_index, int64_t n_nodes, void* keys_sorted,
+                       void* perm, void* ptr, void* workspace, int64_t workspace_bytes,
+                       int idx_dtype, void* stream);
+/* out[i] = in[perm[i]] for 4- or 8-byte elements (elem_bytes), perm has idx_dtype. */
+int b200mp_permute(const void* in, const void* perm, void* out, int64_t n, int elem_bytes,
+                   int idx_dtype, void* stream);
+/* Narrowing / widening copy between index dtypes (int64 <-> int32). */
+int b200mp_convert_index(const void* in, int in_dtype, void* out, int out_dtype, int64_t n,
+                         void* stream);
+/* Self-loop handling.  Output order is the reference's: all non-loop edges in input order, then
+ * (i,i) for i in [0, n_nodes).  w_in/w_out may be NULL.  mode 0 = add_remaining_self_loops
+ * (existing loop weights override fill_value; duplicate loops: the LAST in input order wins,
+ * which is the reference's CPU behaviour), mode 1 = remove_self_loops + add_self_loops(fill).
+ * n_out_dev (DEVICE int64) receives E' = #nonloops + n_nodes.  row_out/col_out/w_out need
+ * n_edges + n_nodes entries.  Workspace from b200mp_self_loops_workspace_bytes(). */
+int64_t b200mp_self_loops_workspace_bytes(int64_t n_edges, int64_t n_nodes, int idx_dtype);
+int b200mp_self_loops(const void* row, const void* col, const float* w_in, int64_t n_edges,
+                      int64_t n_nodes, float fill_value, int mode, void* row_out, void* col_out,
+                      float* w_out, int64_t* n_out_dev, void* workspace, int64_t workspace_bytes,
+                      int idx_dtype, void* stream);
+/* gcn_norm weights on a destination-sorted (CSR over dst) edge list:
+ *   deg[i]  = sum of w over the CSR row i, in order (bit-identical to the reference's CPU
+ *             scatter_add_, which visits edges in input order, because the sort is stable);
+ *   dinv    = deg^-0.5 with inf -> 0;   w_out[e] = dinv[src[e]] * w[e] * dinv[dst(e)].
+ * w may be NULL (all ones).  deg_inv_sqrt (n_nodes floats) is an output too. */
+int b200mp_gcn_norm_csr(const void* rowptr, const void* src, const float* w, int64_t n_nodes,
+                        int64_t n_edges, float* deg_inv_sqrt, float* w_out, int idx_dtype,
+                        void* stream);
+
+/* Long-row plan: rows with more than `chunk` edges are split into chunks of `chunk` edges so no
+ * warp ever walks a power-law hub alone.  Two calls: count (writes counts_dev[2] =
+ * {n_long_rows, n_chunks} to DEVICE memory; the caller reads them back once per graph), then
+ * fill: long_rows[n_long_rows] (ascending row ids) and chunk_ptr[n_long_rows + 1] (exclusive scan
+ * of ceil(deg / chunk)), both int64.  Workspace from b200mp_csr_plan_workspace_bytes(). */
+int b200mp_csr_plan_count(const void* rowptr, int64_t n_rows, int64_t chunk, int64_t* counts_dev,
+                          int idx_dtype, void* stream);
+int64_t b200mp_csr_plan_workspace_bytes(int64_t n_rows, int64_t n_long_rows, int idx_dtype);
+int b200mp_csr_plan_fill(const void* rowptr, int64_t n_rows, int64_t chunk, int64_t n_long_rows,
+                         int64_t* long_rows, int64_t* chunk_ptr, void* workspace,
+                         int64_t workspace_bytes, int idx_dtype, void* stream);
+
+/* ------------------------------------------------------------------ gather + segmented reduce (the hot path)
+ * out[i, :] = REDUCE_{e in [rowptr[i], rowptr[i+1])} val[e] * x[col[e], :]
+ * Replaces: MessagePassing._collect/_lift index_select + message + aggregate
+ * (nn/conv/message_passing.py:263-333,577-595; collect.jinja:118-139; aggr/base.py:173-185),
+ * utils/_spmm.py:12-136, EdgeIndex.matmul (edge_index.py:1903-1970),
+ * torch.ops.torch_sparse.spmm_{sum,mean,min,max} (edge_index.py:1798-1810).
+ * Semantics are the reference's: empty rows -> 0 for every reduce; mean divides by
+ * max(deg, 1); val (fp32, nullable) multiplies before the reduction; the weighted product is
+ * rounded before the add (no FMA contraction) so that rows walked by a single lane group in CSR
+ * order reproduce the reference's CPU results bit for bit.
+ * x: [n_cols, feat], out: [n_rows, feat], both val_dtype.
+ * Long rows: pass the plan (long_rows, chunk_ptr, n_long_rows, n_chunks, chunk) and a partials
+ * workspace of n_chunks * feat fp32, or n_long_rows = 0 to walk every row with one lane group.
+ * bias (nullable, feat fp32) is added to every output row in the epilogue (GCNConv's `out + bias`,
+ * gcn_conv.py:265-266, without a second pass over [N, F]). */
+int b200mp_spmm_csr(const void* rowptr, const void* col, const float* val, const void* x,
+                    void* out, int64_t n_rows, int64_t n_cols, int64_t feat, int reduce,
+                    const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
+                    int64_t n_chunks, int64_t chunk, float* partials, const float* bias,
+                    int idx_dtype, int val_dtype, void* stream);
+
+/* Segmented reduce without gather: out[i,:] = REDUCE_{e in [ptr[i], ptr[i+1])} src[e,:].
+ * Replaces utils/_segment.py:11-50 (torch._segment_reduce / torch_scatter.segment_csr) and the
+ * sorted-index case of utils/_scatter.py:14-138.  Same empty-segment and +-inf -> 0 rules. */
+int b200mp_segment_csr(const void* ptr, const void* src, void* out, int64_t n_rows, int64_t n_src,
+                       int64_t feat, int reduce, int idx_dtype, int val_dtype, void* stream);
+
+/* Backward of min/max aggregation (ATen scatter_reduce rule: the gradient is split evenly among
+ * tied extrema, and the zero-initialised output counts as one more tie when the extremum is
+ * exactly 0 -- see oracle/mp_oracle.c oracle_scatter_backward).  Works on the TRANSPOSED CSR
+ * (rows = source nodes, colT[e] = destination of that edge, valT = its weight):
+ *   grad_x[j,:] = sum_{e in rowT(j)} [valT[e]*x[j,:] == out[colT[e],:]] * valT[e] * g[colT[e],:] / ties[colT[e],:]
+ * ties [n_dst, feat] fp32 is produced by b200mp_minmax_ties on the forward CSR. */
+int b200mp_minmax_ties(const void* rowptr, const void* col, const float* val, const void* x,
+                       const void* out, float* ties, int64_t n_rows, int64_t feat,
+                       int count_self_zero, int idx_dtype, int val_dtype, void* stream);
+int b200mp_minmax_backward(const void* rowptr_t, const void* col_t, const float* val_t,
+                           const void* x, const void* out, const void* grad_out, const float* ties,
+                           void* grad_x, int64_t n_src, int64_t feat, int idx_dtype,
+                           int val_dtype, void* stream);
+
+/* Edge-wise dot product (SDDMM): dot[e] = sum_f a[row_of(e), f] * b[col[e], f] over a CSR.
+ * This is the gradient of b200mp_spmm_csr(sum) wrt val: a = grad_out, b = x.
+ * Replaces the value-gradient branch of _scatter_spmm (edge_index.py:1950-1953). */
+int b200mp_sddmm_csr(const void* rowptr, const void* col, const void* a, const void* b, float* dot,
+                     int64_t n_rows, int64_t feat, int idx_dtype, int val_dtype, void* stream);
+
+/* ------------------------------------------------------------------ COO scatter fallback (atomics)
+ * out[index[e], :] (+)= src[e, :] for an UNSORTED index.  Replaces utils/_scatter.py:14-138
+ * (aten::scatter_add_ / scatter_reduce_, torch_scatter.scatter).  fp32 only.  `count` is a
+ * caller-provided n_rows fp32 scratch (used by mean/min/max to detect empty rows).  out is fully
+ * written (initialised inside).  sum uses red.global.add.v4.f32 where feat % 4 == 0. */
+int b200mp_scatter_coo(const float* src, const void* index, float* out, float* count,
+                       int64_t n_src, int64_t n_rows, int64_t feat, int reduce, int idx_dtype,
+                       void* stream);
+/* Gather rows: out[e,:] = x[index[e],:]  (aten::index_select, message_passing.py:263-290) --
+ * only used by the unfused compatibility path and by backward of scatter. scale (nullable, one
+ * fp32 per row of out) multiplies each gathered row. */
+int b200mp_gather_rows(const void* x, const void* index, const float* scale, void* out,
+                       int64_t n_out, int64_t feat, int idx_dtype, int val_dtype, void* stream);
+
+/* ------------------------------------------------------------------ segment softmax
+ * out[e,h] = exp(src[e,h] - max_g) / (sum_g exp(src - max_g) + 1e-16) over CSR groups.
+ * Replaces utils/_softmax.py:12-92 and pyg_lib.ops.softmax_csr.  fp32.  backward:
+ * grad_src = out * (grad_out - sum_g(grad_out * out)). */
+int b200mp_softmax_csr(const void* ptr, const float* src, float* out, int64_t n_rows,
+                       int64_t n_src, int64_t heads, int idx_dtype, void* stream);
+int b200mp_softmax_csr_backward(const void* ptr, const float* out, const float* grad_out,
+                                float* grad_src, int64_t n_rows, int64_t n_src, int64_t heads,
+                                int idx_dtype, void* stream);
+
+/* ------------------------------------------------------------------ fused GAT attention + aggregation
+ * One sweep over the destination-sorted CSR per (node, head):
+ *   logit_e = leaky_relu(a_src[col[e],h] + a_dst[i,h], slope)
+ *   alpha_e = softmax over the row;  out[i,h,:] = sum_e alpha_e * xh[col[e],h,:]
+ * Replaces GATConv.edge_update + message + aggregate (nn/conv/gat_conv.py:387-409,
+ * utils/_softmax.py:82-88) -- 12 kernels and three [E,H,C] tensors in the reference.
+ * xh: [n_src, heads*chan] val_dtype; a_src [n_src, heads], a_dst [n_rows, heads] fp32;
+ * out: [n_rows, heads*chan] val_dtype; row_max/row_den [n_rows, heads] fp32 (saved for backward);
+ * alpha_out (nullable) [n_edges, heads] fp32 in CSR order. */
+int b200mp_gat_fused_csr(const void* rowptr, const void* col, const void* xh, const float* a_src,
+                         const float* a_dst, void* out, float* row_max, float* row_den,
+                         float* alpha_out, int64_t n_rows, int64_t heads, int64_t chan,
+                         float slope, int idx_dtype, int val_dtype, void* stream);
+/* Backward of b200mp_gat_fused_csr in two sweeps, attention recomputed from row_max/row_den:
+ *  destination sweep (rowptr/col): grad_pre[e,h] (CSR order, scratch [n_edges, heads]) and
+ *      grad_a_dst[i,h];
+ *  source sweep (rowptr_t/col_t, t2csr[e] = CSR slot of transposed slot e): grad_xh[j,h,:] (the
+ *      message term only; the a_src/a_dst terms flow back through the caller's (xh*att).sum(-1))
+ *      and grad_a_src[j,h]. */
+int b200mp_gat_fused_csr_backward(const void* rowptr, const void* col, const void* rowptr_t,
+                                  const void* col_t, const void* t2csr, const void* xh,
+                                  const float* a_src, const float* a_dst, const float* row_max,
+                                  const float* row_den, const void* out, const void* grad_out,
+                                  float* grad_pre, void* grad_xh, float* grad_a_src,
+                                  float* grad_a_dst, int64_t n_rows, int64_t n_src, int64_t heads,
+                                  int64_t chan, float slope, int idx_dtype, int val_dtype,
+                                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MP_H_ */

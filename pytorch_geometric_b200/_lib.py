@@ -1,0 +1,92 @@
+"""ctypes binding of libb200mp.so -- the thin layer between torch tensors and the C ABI.
+
+There is NO CPU fallback and no PyTorch-eager fallback: if the library cannot be loaded (or
+built), importing this module raises.  Every wrapper in ops.py refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+from . import _build
+
+_I64 = ctypes.c_int64
+_INT = ctypes.c_int
+_P = ctypes.c_void_p
+_F = ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/b200mp.h one to one
+_SIGS = {
+    "b200mp_version": (ctypes.c_char_p, []),
+    "b200mp_last_error": (ctypes.c_char_p, []),
+    "b200mp_device_info": (_INT, [_P, _P, _P, _P]),
+    "b200mp_degree": (_INT, [_P, _I64, _I64, _P, _INT, _P]),
+    "b200mp_index2ptr": (_INT, [_P, _I64, _I64, _P, _INT, _P]),
+    "b200mp_ptr2index": (_INT, [_P, _I64, _I64, _P, _INT, _P]),
+    "b200mp_index_stats": (_INT, [_P, _I64, _P, _INT, _P]),
+    "b200mp_sort_workspace_bytes": (_I64, [_I64, _I64, _INT]),
+    "b200mp_sort_by_key": (_INT, [_P, _I64, _I64, _P, _P, _P, _P, _I64, _INT, _P]),
+    "b200mp_permute": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P]),
+    "b200mp_convert_index": (_INT, [_P, _INT, _P, _INT, _I64, _P]),
+    "b200mp_self_loops_workspace_bytes": (_I64, [_I64, _I64, _INT]),
+    "b200mp_self_loops": (_INT, [_P, _P, _P, _I64, _I64, _F, _INT, _P, _P, _P, _P, _P, _I64, _INT, _P]),
+    "b200mp_gcn_norm_csr": (_INT, [_P, _P, _P, _I64, _I64, _P, _P, _INT, _P]),
+    "b200mp_csr_plan_count": (_INT, [_P, _I64, _I64, _P, _INT, _P]),
+    "b200mp_csr_plan_workspace_bytes": (_I64, [_I64, _I64, _INT]),
+    "b200mp_csr_plan_fill": (_INT, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _INT, _P]),
+    "b200mp_spmm_csr": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _I64, _I64, _I64, _P,
+                               _P, _INT, _INT, _P]),
+    "b200mp_segment_csr": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _INT, _INT, _P]),
+    "b200mp_minmax_ties": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _INT, _P]),
+    "b200mp_minmax_backward": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
+    "b200mp_sddmm_csr": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
+    "b200mp_scatter_coo": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _INT, _INT, _P]),
+    "b200mp_gather_rows": (_INT, [_P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
+    "b200mp_softmax_csr": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P]),
+    "b200mp_softmax_csr_backward": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _INT, _P]),
+    "b200mp_gat_fused_csr": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _F, _INT, _INT, _P]),
+    "b200mp_gat_fused_csr_backward": (_INT, [_P] * 16 + [_I64, _I64, _I64, _I64, _F, _INT, _INT, _P]),
+}
+
+_lib = None
+
+
+def header_symbols() -> list[str]:
+    """Every function declared in include/b200mp.h (used by the symbol-export test)."""
+    with open(os.path.join(_build.INCLUDE, "b200mp.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200mp_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if _build.needs_build():
+            try:
+                path = _build.build()
+            except Exception as exc:  # no silent fallback
+                if not os.path.exists(_build.LIB):
+                    raise RuntimeError(
+                        "pytorch_geometric_b200: libb200mp.so is missing and could not be built "
+                        f"({exc}); there is no CPU / eager fallback.") from exc
+                path = _build.LIB
+        l = ctypes.CDLL(path)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+class B200MPError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().b200mp_last_error().decode()
+        raise B200MPError(f"{what or 'b200mp'} failed (code {rc}): {msg}")

@@ -1,0 +1,31 @@
+// segment.cu -- C ABI for the segmented reduce without gather (b200mp_segment_csr).
+#include "csr_reduce.cuh"
+
+using namespace b200mp;
+
+namespace b200mp {
+template <typename T, typename I>
+int segment_typed(const void* ptr, const void* src, void* out, int64_t n_rows, int64_t feat, int reduce,
+                  cudaStream_t stream) {
+    LongRowPlan plan{nullptr, nullptr, 0, 0, 0, nullptr};
+    return csr_reduce_by_op<T, I, false>(static_cast<const I*>(ptr), static_cast<const I*>(nullptr), nullptr,
+                                         static_cast<const T*>(src), static_cast<T*>(out), n_rows, feat,
+                                         reduce, true, plan, nullptr, stream);
+}
+}  // namespace b200mp
+
+extern "C" int b200mp_segment_csr(const void* ptr, const void* src, void* out, int64_t n_rows,
+                                  int64_t n_src, int64_t feat, int reduce, int idx_dtype, int val_dtype,
+                                  void* stream) {
+    B200MP_CHECK_ARG(n_rows >= 0 && n_src >= 0 && feat >= 0);
+    if (n_rows == 0 || feat == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(ptr && out);
+    B200MP_CHECK_ARG(src || n_src == 0);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (val_dtype == B200MP_F32 && idx_dtype == B200MP_I32) return segment_typed<float, int32_t>(ptr, src, out, n_rows, feat, reduce, s);
+    if (val_dtype == B200MP_F32 && idx_dtype == B200MP_I64) return segment_typed<float, int64_t>(ptr, src, out, n_rows, feat, reduce, s);
+    if (val_dtype == B200MP_BF16 && idx_dtype == B200MP_I32) return segment_typed<__nv_bfloat16, int32_t>(ptr, src, out, n_rows, feat, reduce, s);
+    if (val_dtype == B200MP_BF16 && idx_dtype == B200MP_I64) return segment_typed<__nv_bfloat16, int64_t>(ptr, src, out, n_rows, feat, reduce, s);
+    set_error("segment_csr: unsupported dtype combination val=%d idx=%d", val_dtype, idx_dtype);
+    return B200MP_ERR_UNSUPPORTED;
+}

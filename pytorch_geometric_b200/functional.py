@@ -1,0 +1,200 @@
+"""Differentiable front ends of the hot path (custom autograd over the C-ABI kernels).
+
+`aggregate(graph, x, reduce, edge_weight)` is the fused replacement for the reference's
+collect -> message -> aggregate sequence (nn/conv/message_passing.py:421-563) and for
+`EdgeIndex.matmul` / `spmm` (edge_index.py:1925-1970, utils/_spmm.py:12-136).
+Backward follows `_TorchSPMM.backward` (edge_index.py:1860-1900): the same kernel on the
+transposed CSR; min/max use the ATen tie rule (oracle_scatter_backward in oracle/mp_oracle.c).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from .graph import CSRGraph
+
+
+class _Aggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, edge_weight: Optional[Tensor], graph: CSRGraph, reduce: str):
+        val = graph.val
+        if edge_weight is not None:
+            val = graph.to_csr_order(edge_weight.detach().float().contiguous().view(-1))
+        out = ops.spmm_csr(graph.rowptr, graph.col, val, x, graph.num_dst, reduce, graph.plan)
+        ctx.graph, ctx.reduce = graph, reduce
+        ctx.has_ew = edge_weight is not None
+        need_x = reduce in ("min", "max") or (ctx.has_ew and edge_weight.requires_grad)
+        ctx.save_for_backward(x if need_x else None, out if reduce in ("min", "max") else None, val)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        graph, reduce = ctx.graph, ctx.reduce
+        x, out, val = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        graph.build_transpose()
+        gx = gw = None
+        val_t = None
+        if val is not None:
+            val_t = graph.val_t if (not ctx.has_ew and graph.val_t is not None) else \
+                graph.to_csc_order(graph.from_csr_order(val))
+        if ctx.needs_input_grad[0]:
+            if reduce in ("sum", "add"):
+                gx = ops.spmm_csr(graph.rowptr_t, graph.col_t, val_t, grad_out, graph.num_src, "sum", graph.plan_t)
+            elif reduce == "mean":
+                mv = graph.mean_val_t()
+                if val_t is not None:
+                    mv = mv * val_t
+                gx = ops.spmm_csr(graph.rowptr_t, graph.col_t, mv, grad_out, graph.num_src, "sum", graph.plan_t)
+            else:  # min / max
+                ties = ops.minmax_ties(graph.rowptr, graph.col, val, x, out, count_self_zero=True)
+                gx = ops.minmax_backward(graph.rowptr_t, graph.col_t, val_t, x, out, grad_out, ties)
+        if ctx.has_ew and ctx.needs_input_grad[1]:
+            if reduce not in ("sum", "add", "mean"):
+                raise NotImplementedError("gradient wrt edge_weight is implemented for sum/mean only")
+            g = grad_out
+            dot = ops.sddmm_csr(graph.rowptr, graph.col, g, x)          # CSR order
+            if reduce == "mean":
+                inv = 1.0 / graph.in_degree().clamp(min=1).to(torch.float32)
+                dot = dot * ops.gather_rows(inv.view(-1, 1), graph.dst_csr).view(-1)
+            gw = graph.from_csr_order(dot)
+        return gx, gw, None, None
+
+
+def aggregate(graph: CSRGraph, x: Tensor, reduce: str = "sum", edge_weight: Optional[Tensor] = None) -> Tensor:
+    """out[i] = REDUCE_{(j -> i)} w_ji * x[j]; x: [num_src, F] -> [num_dst, F].
+
+    `edge_weight` (original edge order, may require grad) overrides the static values cached in
+    the graph (e.g. gcn_norm weights).  Empty destinations give 0 for every reduce.
+    """
+    if reduce not in ("sum", "add", "mean", "min", "max"):
+        raise ValueError(f"Encountered invalid `reduce` argument '{reduce}'")
+    if x.dim() == 1:
+        return aggregate(graph, x.view(-1, 1), reduce, edge_weight).view(-1)
+    if x.dim() > 2:
+        shape = x.shape[1:]
+        return aggregate(graph, x.reshape(x.size(0), -1), reduce, edge_weight).view((graph.num_dst, ) + shape)
+    if x.size(0) != graph.num_src:
+        raise ValueError(f"x has {x.size(0)} rows but the graph has {graph.num_src} source nodes")
+    return _Aggregate.apply(x, edge_weight, graph, reduce)
+
+
+class _Segment(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src: Tensor, ptr: Tensor, reduce: str):
+        out = ops.segment_csr(src, ptr, reduce)
+        ctx.reduce = reduce
+        ctx.save_for_backward(ptr, src if reduce in ("min", "max") else None, out if reduce in ("min", "max") else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        ptr, src, out = ctx.saved_tensors
+        reduce = ctx.reduce
+        n_src = int(ptr[-1])
+        index = ops.ptr2index(ptr, n_src)
+        g2 = grad_out.contiguous().view(grad_out.size(0), -1)
+        if reduce in ("sum", "add"):
+            g = ops.gather_rows(g2, index)
+        elif reduce == "mean":
+            inv = 1.0 / (ptr[1:] - ptr[:-1]).clamp(min=1).to(torch.float32)
+            g = ops.gather_rows(g2, index, ops.gather_rows(inv.view(-1, 1), index).view(-1))
+        else:
+            # _segment_reduce backward: even split among ties (no zero-initialised self here)
+            s2, o2 = src.view(src.size(0), -1), out.view(out.size(0), -1)
+            eq = (s2 == ops.gather_rows(o2, index)).to(s2.dtype)
+            ties = ops.segment_csr(eq, ptr, "sum")
+            g = eq * ops.gather_rows(g2 / ties.clamp(min=1), index)
+        return g.view((n_src, ) + tuple(grad_out.shape[1:])), None, None
+
+
+def segment(src: Tensor, ptr: Tensor, reduce: str = "sum") -> Tensor:
+    return _Segment.apply(src, ptr, reduce)
+
+
+class _ScatterCOO(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src: Tensor, index: Tensor, dim_size: int, reduce: str):
+        out = ops.scatter_coo(src, index, dim_size, reduce)
+        ctx.reduce, ctx.dim_size = reduce, dim_size
+        keep = reduce in ("min", "max", "mul")
+        ctx.save_for_backward(index, src if keep else None, out if keep else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        index, src, out = ctx.saved_tensors
+        reduce = ctx.reduce
+        g2 = grad_out.contiguous().view(grad_out.size(0), -1)
+        if reduce in ("sum", "add"):
+            g = ops.gather_rows(g2, index)                       # scatter_add_ backward == gather
+        elif reduce == "mean":
+            cnt = ops.degree(index, ctx.dim_size).clamp(min=1).to(torch.float32)
+            g = ops.gather_rows(g2, index, ops.gather_rows((1.0 / cnt).view(-1, 1), index).view(-1))
+        elif reduce in ("min", "max"):
+            s2, o2 = src.view(src.size(0), -1), out.view(out.size(0), -1)
+            eq = (s2 == ops.gather_rows(o2, index)).to(torch.float32)
+            # ATen scatter_reduce rule incl. the zero-initialised `self` tie (oracle_scatter_backward)
+            ties = ops.scatter_coo(eq, index, ctx.dim_size, "sum") + (o2 == 0).to(torch.float32)
+            g = eq * ops.gather_rows(g2 / ties, index)
+        else:
+            raise NotImplementedError("backward of scatter(reduce='mul') is not implemented")
+        return g.view((index.numel(), ) + tuple(grad_out.shape[1:])), None, None, None
+
+
+def scatter_coo(src: Tensor, index: Tensor, dim_size: int, reduce: str = "sum") -> Tensor:
+    return _ScatterCOO.apply(src, index, dim_size, reduce)
+
+
+class _SoftmaxCSR(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src: Tensor, ptr: Tensor):
+        out = ops.softmax_csr(src, ptr)
+        ctx.save_for_backward(out, ptr)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        out, ptr = ctx.saved_tensors
+        return ops.softmax_csr_backward(out, grad_out, ptr), None
+
+
+def softmax_csr(src: Tensor, ptr: Tensor) -> Tensor:
+    return _SoftmaxCSR.apply(src, ptr)
+
+
+class _GATFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xh: Tensor, a_src: Tensor, a_dst: Tensor, graph: CSRGraph, heads: int, chan: int, slope: float,
+                want_alpha: bool):
+        out, row_max, row_den, alpha = ops.gat_fused_csr(graph.rowptr, graph.col, xh, a_src, a_dst, heads, chan,
+                                                         slope, want_alpha)
+        ctx.graph, ctx.dims = graph, (heads, chan, slope)
+        ctx.save_for_backward(xh, a_src, a_dst, row_max, row_den, out)
+        if alpha is None:
+            alpha = xh.new_empty(0)
+        ctx.mark_non_differentiable(alpha)
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor, _grad_alpha):
+        xh, a_src, a_dst, row_max, row_den, out = ctx.saved_tensors
+        graph = ctx.graph
+        heads, chan, slope = ctx.dims
+        graph.build_transpose()
+        gxh, gas, gad = ops.gat_fused_csr_backward(graph.rowptr, graph.col, graph.rowptr_t, graph.col_t, graph.t2csr,
+                                                   xh, a_src.float().contiguous(), a_dst.float().contiguous(),
+                                                   row_max, row_den, out, grad_out, heads, chan, slope)
+        return gxh, gas.to(a_src.dtype), gad.to(a_dst.dtype), None, None, None, None, None
+
+
+def gat_attention(graph: CSRGraph, xh: Tensor, a_src: Tensor, a_dst: Tensor, heads: int, chan: int,
+                  negative_slope: float = 0.2, return_alpha: bool = False):
+    """out[i,h,:] = sum_e softmax_i(leaky_relu(a_src[j,h] + a_dst[i,h]))_e * xh[j,h,:]
+    (GATConv.edge_update + message + aggregate, gat_conv.py:387-409) in one fused sweep.
+    xh: [num_src, H*C]; returns out [num_dst, H*C] (and alpha [E, H] in CSR order)."""
+    out, alpha = _GATFused.apply(xh, a_src, a_dst, graph, heads, chan, float(negative_slope), return_alpha)
+    return (out, alpha) if return_alpha else out

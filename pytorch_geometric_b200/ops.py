@@ -1,0 +1,405 @@
+"""Tensor-level wrappers over the C ABI (include/b200mp.h).  No autograd here (see functional.py).
+
+PyTorch is used for device memory (the caching allocator owns every buffer) and the current
+stream; all arithmetic happens in libb200mp.so.  Every function refuses non-CUDA tensors: there is
+no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from ._lib import check, lib
+
+F32, BF16 = 0, 1
+I32, I64 = 0, 1
+REDUCE = {"sum": 0, "add": 0, "mean": 1, "min": 2, "amin": 2, "max": 3, "amax": 3, "mul": 4}
+
+
+class _Launches:
+    """Number of engine kernels launched so far (bench.py reports the delta as gpu_launches)."""
+    count = 0
+
+
+LAUNCHES = _Launches()
+
+
+class _Profile:
+    """Optional per-op CUDA-event timing on the launching stream (bench.py's roofline numbers).
+    Disabled by default: zero overhead on the product path."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+
+    def reset(self, enabled: bool = False):
+        self.enabled = enabled
+        self.events = {}
+
+    def begin(self, name: str):
+        if not self.enabled:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.events.setdefault(name, []).append((e0, e1))
+        return e1
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        return {k: {"ms_total": sum(a.elapsed_time(b) for a, b in v), "calls": len(v)} for k, v in self.events.items()}
+
+
+PROFILE = _Profile()
+
+
+def _timed(name: str, n_kernels: int, fn, *args):
+    LAUNCHES.count += n_kernels
+    end = PROFILE.begin(name)
+    rc = fn(*args)
+    if end is not None:
+        end.record()
+    check(rc, name)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pytorch_geometric_b200 ops run on CUDA tensors only (no CPU fallback); "
+                               f"got a tensor on {t.device}")
+
+
+def _idt(t: Tensor) -> int:
+    if t.dtype == torch.int32:
+        return I32
+    if t.dtype == torch.int64:
+        return I64
+    raise TypeError(f"index tensors must be int32 or int64, got {t.dtype}")
+
+
+def _vdt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"feature tensors must be float32 or bfloat16, got {t.dtype}")
+
+
+def _same_idx(*ts: Optional[Tensor]) -> int:
+    ds = {t.dtype for t in ts if t is not None}
+    if len(ds) != 1:
+        raise TypeError(f"index tensors of one call must share a dtype, got {ds}")
+    return _idt(next(t for t in ts if t is not None))
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------ structure
+def degree(index: Tensor, num_nodes: int) -> Tensor:
+    _cuda(index)
+    index = index.contiguous()
+    deg = torch.empty(num_nodes, dtype=index.dtype, device=index.device)
+    check(lib().b200mp_degree(_p(index), index.numel(), num_nodes, _p(deg), _idt(index), _stream()), "degree")
+    return deg
+
+
+def index2ptr(index: Tensor, size: int) -> Tensor:
+    _cuda(index)
+    index = index.contiguous()
+    ptr = torch.empty(size + 1, dtype=index.dtype, device=index.device)
+    check(lib().b200mp_index2ptr(_p(index), index.numel(), size, _p(ptr), _idt(index), _stream()), "index2ptr")
+    return ptr
+
+
+def ptr2index(ptr: Tensor, output_size: Optional[int] = None) -> Tensor:
+    _cuda(ptr)
+    ptr = ptr.contiguous()
+    n = int(ptr[-1]) if output_size is None else int(output_size)
+    index = torch.empty(n, dtype=ptr.dtype, device=ptr.device)
+    check(lib().b200mp_ptr2index(_p(ptr), ptr.numel() - 1, n, _p(index), _idt(ptr), _stream()), "ptr2index")
+    return index
+
+
+def index_stats(index: Tensor) -> Tuple[int, int, bool]:
+    """(min, max, is_sorted) of an index tensor -- one kernel + one D2H read."""
+    _cuda(index)
+    index = index.contiguous()
+    st = torch.empty(3, dtype=torch.int64, device=index.device)
+    check(lib().b200mp_index_stats(_p(index), index.numel(), _p(st), _idt(index), _stream()), "index_stats")
+    mn, mx, srt = st.tolist()
+    return mn, mx, bool(srt)
+
+
+def sort_by_key(keys: Tensor, num_nodes: int, want_sorted: bool = True,
+                want_ptr: bool = True) -> Tuple[Optional[Tensor], Tensor, Optional[Tensor]]:
+    """Stable sort of keys in [0, num_nodes): (keys_sorted, perm, ptr)."""
+    _cuda(keys)
+    keys = keys.contiguous()
+    n = keys.numel()
+    it = _idt(keys)
+    ws = _ws(lib().b200mp_sort_workspace_bytes(n, num_nodes, it), keys.device)
+    ks = torch.empty_like(keys) if want_sorted else None
+    perm = torch.empty_like(keys)
+    ptr = torch.empty(num_nodes + 1, dtype=keys.dtype, device=keys.device) if want_ptr else None
+    check(lib().b200mp_sort_by_key(_p(keys), n, num_nodes, _p(ks), _p(perm), _p(ptr), _p(ws), ws.numel(), it,
+                                   _stream()), "sort_by_key")
+    return ks, perm, ptr
+
+
+def permute(src: Tensor, perm: Tensor) -> Tensor:
+    """out[i] = src[perm[i]] for 1-D tensors of 4- or 8-byte elements."""
+    _cuda(src, perm)
+    src, perm = src.contiguous(), perm.contiguous()
+    out = torch.empty(perm.numel(), dtype=src.dtype, device=src.device)
+    check(lib().b200mp_permute(_p(src), _p(perm), _p(out), perm.numel(), src.element_size(), _idt(perm),
+                               _stream()), "permute")
+    return out
+
+
+def convert_index(index: Tensor, dtype: torch.dtype) -> Tensor:
+    _cuda(index)
+    if index.dtype == dtype:
+        return index
+    index = index.contiguous()
+    out = torch.empty(index.shape, dtype=dtype, device=index.device)
+    check(lib().b200mp_convert_index(_p(index), _idt(index), _p(out), _idt(out), index.numel(), _stream()),
+          "convert_index")
+    return out
+
+
+def self_loops(row: Tensor, col: Tensor, weight: Optional[Tensor], num_nodes: int, fill_value: float = 1.0,
+               mode: int = 0) -> Tuple[Tensor, Tensor, Optional[Tensor]]:
+    """mode 0: add_remaining_self_loops; mode 1: remove_self_loops + add_self_loops."""
+    _cuda(row, col, weight)
+    row, col = row.contiguous(), col.contiguous()
+    it = _same_idx(row, col)
+    E = row.numel()
+    if weight is not None:
+        weight = weight.contiguous().float()
+    ws = _ws(lib().b200mp_self_loops_workspace_bytes(E, num_nodes, it), row.device)
+    r2 = torch.empty(E + num_nodes, dtype=row.dtype, device=row.device)
+    c2 = torch.empty_like(r2)
+    w2 = torch.empty(E + num_nodes, dtype=torch.float32, device=row.device) if weight is not None else None
+    n_out = torch.empty(1, dtype=torch.int64, device=row.device)
+    check(lib().b200mp_self_loops(_p(row), _p(col), _p(weight), E, num_nodes, float(fill_value), mode, _p(r2),
+                                  _p(c2), _p(w2), _p(n_out), _p(ws), ws.numel(), it, _stream()), "self_loops")
+    n = int(n_out.item())  # one D2H sync, as the reference's boolean-mask indexing has
+    return r2[:n], c2[:n], (w2[:n] if w2 is not None else None)
+
+
+def gcn_norm_csr(rowptr: Tensor, src: Tensor, weight: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """(deg_inv_sqrt [N], normalised weights [E]) on a destination-sorted CSR."""
+    _cuda(rowptr, src, weight)
+    it = _same_idx(rowptr, src)
+    N, E = rowptr.numel() - 1, src.numel()
+    dinv = torch.empty(N, dtype=torch.float32, device=rowptr.device)
+    w_out = torch.empty(E, dtype=torch.float32, device=rowptr.device)
+    check(lib().b200mp_gcn_norm_csr(_p(rowptr), _p(src), _p(weight), N, E, _p(dinv), _p(w_out), it, _stream()),
+          "gcn_norm_csr")
+    return dinv, w_out
+
+
+class LongRowPlan:
+    """Rows with more than `chunk` edges, cut into chunks (b200mp_csr_plan_*)."""
+
+    __slots__ = ("long_rows", "chunk_ptr", "n_long", "n_chunks", "chunk", "_partials")
+
+    def __init__(self, rowptr: Tensor, chunk: int):
+        _cuda(rowptr)
+        it = _idt(rowptr)
+        n_rows = rowptr.numel() - 1
+        counts = torch.empty(2, dtype=torch.int64, device=rowptr.device)
+        check(lib().b200mp_csr_plan_count(_p(rowptr), n_rows, chunk, _p(counts), it, _stream()), "csr_plan_count")
+        self.n_long, self.n_chunks = (int(v) for v in counts.tolist())
+        self.chunk = int(chunk)
+        self.long_rows = self.chunk_ptr = None
+        self._partials = None
+        if self.n_long:
+            self.long_rows = torch.empty(self.n_long, dtype=torch.int64, device=rowptr.device)
+            self.chunk_ptr = torch.empty(self.n_long + 1, dtype=torch.int64, device=rowptr.device)
+            ws = _ws(lib().b200mp_csr_plan_workspace_bytes(n_rows, self.n_long, it), rowptr.device)
+            check(lib().b200mp_csr_plan_fill(_p(rowptr), n_rows, chunk, self.n_long, _p(self.long_rows),
+                                             _p(self.chunk_ptr), _p(ws), ws.numel(), it, _stream()),
+                  "csr_plan_fill")
+
+    def partials(self, feat: int, device) -> Optional[Tensor]:
+        if not self.n_long:
+            return None
+        need = self.n_chunks * feat
+        if self._partials is None or self._partials.numel() < need:
+            self._partials = torch.empty(need, dtype=torch.float32, device=device)
+        return self._partials
+
+
+# ------------------------------------------------------------------ the hot path
+def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_rows: int, reduce: str = "sum",
+             plan: Optional[LongRowPlan] = None, out: Optional[Tensor] = None,
+             bias: Optional[Tensor] = None) -> Tensor:
+    """out[i,:] = REDUCE_{e in row i} val[e] * x[col[e],:] (+ bias)  (x: [n_cols, F] contiguous)."""
+    _cuda(rowptr, col, val, x)
+    if x.dim() != 2:
+        raise ValueError("spmm_csr expects a 2-D feature matrix")
+    x = x.contiguous()
+    it = _same_idx(rowptr, col)
+    if val is not None and (val.dtype != torch.float32 or not val.is_contiguous()):
+        val = val.contiguous().float()
+    F = x.size(1)
+    if out is None:
+        out = torch.empty(n_rows, F, dtype=x.dtype, device=x.device)
+    if plan is not None and plan.n_long:
+        part = plan.partials(F, x.device)
+        args = (_p(plan.long_rows), _p(plan.chunk_ptr), plan.n_long, plan.n_chunks, plan.chunk, _p(part))
+    else:
+        args = (None, None, 0, 0, 0, None)
+    if bias is not None:
+        _cuda(bias)
+        if bias.dtype != torch.float32 or not bias.is_contiguous():
+            bias = bias.detach().float().contiguous()
+        if bias.numel() != F:
+            raise ValueError("bias must have one entry per feature")
+    _timed("spmm_csr", 2 if args[2] else 1, lib().b200mp_spmm_csr, _p(rowptr), _p(col), _p(val), _p(x), _p(out),
+           n_rows, x.size(0), F, REDUCE[reduce], *args, _p(bias), it, _vdt(x), _stream())
+    return out
+
+
+def segment_csr(src: Tensor, ptr: Tensor, reduce: str = "sum") -> Tensor:
+    _cuda(src, ptr)
+    src = src.contiguous()
+    n_rows = ptr.numel() - 1
+    flat = src.view(src.size(0), -1)
+    out = torch.empty((n_rows, flat.size(1)), dtype=src.dtype, device=src.device)
+    check(lib().b200mp_segment_csr(_p(ptr), _p(flat), _p(out), n_rows, flat.size(0), flat.size(1), REDUCE[reduce],
+                                   _idt(ptr), _vdt(src), _stream()), "segment_csr")
+    return out.view((n_rows, ) + tuple(src.shape[1:]))
+
+
+def minmax_ties(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, out: Tensor,
+                count_self_zero: bool = True) -> Tensor:
+    _cuda(rowptr, col, val, x, out)
+    it = _same_idx(rowptr, col)
+    ties = torch.empty(out.shape, dtype=torch.float32, device=out.device)
+    check(lib().b200mp_minmax_ties(_p(rowptr), _p(col), _p(val), _p(x), _p(out), _p(ties), out.size(0),
+                                   out.size(1), int(count_self_zero), it, _vdt(x), _stream()), "minmax_ties")
+    return ties
+
+
+def minmax_backward(rowptr_t: Tensor, col_t: Tensor, val_t: Optional[Tensor], x: Tensor, out: Tensor,
+                    grad_out: Tensor, ties: Tensor) -> Tensor:
+    _cuda(rowptr_t, col_t, val_t, x, out, grad_out, ties)
+    it = _same_idx(rowptr_t, col_t)
+    gx = torch.empty_like(x)
+    check(lib().b200mp_minmax_backward(_p(rowptr_t), _p(col_t), _p(val_t), _p(x), _p(out), _p(grad_out),
+                                       _p(ties), _p(gx), x.size(0), x.size(1), it, _vdt(x), _stream()),
+          "minmax_backward")
+    return gx
+
+
+def sddmm_csr(rowptr: Tensor, col: Tensor, a: Tensor, b: Tensor) -> Tensor:
+    """dot[e] = <a[row(e),:], b[col[e],:]> in CSR edge order."""
+    _cuda(rowptr, col, a, b)
+    it = _same_idx(rowptr, col)
+    a, b = a.contiguous(), b.contiguous()
+    dot = torch.empty(col.numel(), dtype=torch.float32, device=a.device)
+    check(lib().b200mp_sddmm_csr(_p(rowptr), _p(col), _p(a), _p(b), _p(dot), rowptr.numel() - 1, a.size(1), it,
+                                 _vdt(a), _stream()), "sddmm_csr")
+    return dot
+
+
+def scatter_coo(src: Tensor, index: Tensor, n_rows: int, reduce: str = "sum") -> Tensor:
+    """Atomic COO fallback for an unsorted index; fp32, src: [E, F]."""
+    _cuda(src, index)
+    if src.dtype != torch.float32:
+        raise TypeError("scatter_coo is fp32 only (use the CSR path for bf16)")
+    src, index = src.contiguous(), index.contiguous()
+    flat = src.view(src.size(0), -1)
+    out = torch.empty((n_rows, flat.size(1)), dtype=torch.float32, device=src.device)
+    count = torch.empty(n_rows, dtype=torch.float32, device=src.device) if REDUCE[reduce] in (1, 2, 3) else None
+    check(lib().b200mp_scatter_coo(_p(flat), _p(index), _p(out), _p(count), flat.size(0), n_rows, flat.size(1),
+                                   REDUCE[reduce], _idt(index), _stream()), "scatter_coo")
+    return out.view((n_rows, ) + tuple(src.shape[1:]))
+
+
+def gather_rows(x: Tensor, index: Tensor, scale: Optional[Tensor] = None) -> Tensor:
+    _cuda(x, index, scale)
+    x, index = x.contiguous(), index.contiguous()
+    flat = x.view(x.size(0), -1)
+    out = torch.empty((index.numel(), flat.size(1)), dtype=x.dtype, device=x.device)
+    check(lib().b200mp_gather_rows(_p(flat), _p(index), _p(scale), _p(out), index.numel(), flat.size(1),
+                                   _idt(index), _vdt(x), _stream()), "gather_rows")
+    return out.view((index.numel(), ) + tuple(x.shape[1:]))
+
+
+def softmax_csr(src: Tensor, ptr: Tensor) -> Tensor:
+    _cuda(src, ptr)
+    src = src.contiguous().float()
+    flat = src.view(src.size(0), -1)
+    out = torch.empty_like(flat)
+    check(lib().b200mp_softmax_csr(_p(ptr), _p(flat), _p(out), ptr.numel() - 1, flat.size(0), flat.size(1),
+                                   _idt(ptr), _stream()), "softmax_csr")
+    return out.view(src.shape)
+
+
+def softmax_csr_backward(out: Tensor, grad_out: Tensor, ptr: Tensor) -> Tensor:
+    _cuda(out, grad_out, ptr)
+    out, grad_out = out.contiguous(), grad_out.contiguous().float()
+    flat = out.view(out.size(0), -1)
+    g = torch.empty_like(flat)
+    check(lib().b200mp_softmax_csr_backward(_p(ptr), _p(flat), _p(grad_out), _p(g), ptr.numel() - 1, flat.size(0),
+                                            flat.size(1), _idt(ptr), _stream()), "softmax_csr_backward")
+    return g.view(out.shape)
+
+
+def gat_fused_csr(rowptr: Tensor, col: Tensor, xh: Tensor, a_src: Tensor, a_dst: Tensor, heads: int, chan: int,
+                  slope: float, want_alpha: bool = False):
+    """Fused GAT forward: returns (out [n_rows, H*C], row_max, row_den, alpha or None)."""
+    _cuda(rowptr, col, xh, a_src, a_dst)
+    it = _same_idx(rowptr, col)
+    xh = xh.contiguous()
+    a_src, a_dst = a_src.contiguous().float(), a_dst.contiguous().float()
+    n_rows = rowptr.numel() - 1
+    out = torch.empty((n_rows, heads * chan), dtype=xh.dtype, device=xh.device)
+    row_max = torch.empty((n_rows, heads), dtype=torch.float32, device=xh.device)
+    row_den = torch.empty_like(row_max)
+    alpha = torch.empty((col.numel(), heads), dtype=torch.float32, device=xh.device) if want_alpha else None
+    check(lib().b200mp_gat_fused_csr(_p(rowptr), _p(col), _p(xh), _p(a_src), _p(a_dst), _p(out), _p(row_max),
+                                     _p(row_den), _p(alpha), n_rows, heads, chan, float(slope), it, _vdt(xh),
+                                     _stream()), "gat_fused_csr")
+    return out, row_max, row_den, alpha
+
+
+def gat_fused_csr_backward(rowptr, col, rowptr_t, col_t, t2csr, xh, a_src, a_dst, row_max, row_den, out, grad_out,
+                           heads: int, chan: int, slope: float):
+    """Returns (grad_xh [n_src, H*C], grad_a_src [n_src, H], grad_a_dst [n_rows, H])."""
+    _cuda(rowptr, col, rowptr_t, col_t, t2csr, xh, grad_out)
+    it = _same_idx(rowptr, col, rowptr_t, col_t, t2csr)
+    grad_out = grad_out.contiguous()
+    n_rows, n_src = rowptr.numel() - 1, rowptr_t.numel() - 1
+    grad_pre = torch.empty((col.numel(), heads), dtype=torch.float32, device=xh.device)
+    gxh = torch.empty_like(xh)
+    gas = torch.empty((n_src, heads), dtype=torch.float32, device=xh.device)
+    gad = torch.empty((n_rows, heads), dtype=torch.float32, device=xh.device)
+    check(lib().b200mp_gat_fused_csr_backward(_p(rowptr), _p(col), _p(rowptr_t), _p(col_t), _p(t2csr), _p(xh),
+                                              _p(a_src), _p(a_dst), _p(row_max), _p(row_den), _p(out),
+                                              _p(grad_out), _p(grad_pre), _p(gxh), _p(gas), _p(gad), n_rows, n_src,
+                                              heads, chan, float(slope), it, _vdt(xh), _stream()),
+          "gat_fused_csr_backward")
+    return gxh, gas, gad
+
+
+def device_info() -> dict:
+    import ctypes
+    sm, ma, mi, l2 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+    check(lib().b200mp_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(l2)))
+    return {"sm_count": sm.value, "cc": (ma.value, mi.value), "l2_bytes": l2.value}
