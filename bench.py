@@ -101,11 +101,12 @@ def synth_graph(num_nodes: int, num_edges: int, seed: int, device, lo: int = 0, 
     `total_nodes` (the halo)."""
     g = torch.Generator(device=device).manual_seed(seed)
     u = torch.rand(num_edges, device=device, generator=g, dtype=torch.float64)
-    alpha = 2.1
-    # rank ~ Pareto: P(rank > r) ~ r^-(alpha-1), truncated to [1, num_nodes]
-    rank = torch.clamp((1.0 - u * (1.0 - float(num_nodes) ** (1.0 - alpha))) ** (-1.0 / (alpha - 1.0)), max=float(num_nodes))
+    gamma = 2.1                       # in-degree distribution P(deg = k) ~ k^-gamma
+    s = 1.0 / (gamma - 1.0)           # <=> rank-frequency law f(rank) ~ rank^-s (s = 0.909)
+    # inverse CDF of the continuous rank law on [1, num_nodes]: F(r) = (r^(1-s) - 1) / (n^(1-s) - 1)
+    rank = (1.0 + u * (float(num_nodes) ** (1.0 - s) - 1.0)) ** (1.0 / (1.0 - s))
     rank = (rank.long() - 1).clamp_(0, num_nodes - 1)
-    dst = (rank * 2654435761 + 12345) % num_nodes + lo               # scatter hubs over the id range
+    dst = torch.randperm(num_nodes, device=device, generator=g)[rank] + lo   # scatter hubs over the id range
     total = total_nodes if total_nodes is not None else num_nodes
     src_local = torch.randint(0, num_nodes, (num_edges, ), device=device, generator=g) + lo
     if p_local >= 1.0 or total == num_nodes:
@@ -213,6 +214,7 @@ def run_b200(args):
     from pytorch_geometric_b200.nn import GCNConv
 
     N, E, F = args.nodes, args.edges, args.feat
+    ops.set_option("spmm_impl", args.spmm_impl)
     torch.manual_seed(1234 + rank)
     conv = GCNConv(F, F, cached=True).to(dev)
     with torch.no_grad():
@@ -347,7 +349,8 @@ def run_b200(args):
                        "l2_policy": "inputs (x, grad, CSR > 10 GB) are far larger than the 126 MB L2; no explicit flush",
                        "parallelism": "single GPU" if world == 1 else f"node-range sharding x{world}, p_local={args.p_local}, halo all_to_all",
                        "gemm": "torch.nn.functional.linear (cuBLAS fp32, allow_tf32=False)",
-                       "long_rows": graph.plan.n_long, "chunks": graph.plan.n_chunks},
+                       "long_rows": graph.plan.n_long, "chunks": graph.plan.n_chunks,
+                       "spmm_impl": {0: "auto (TMA streaming kernel for 512 B..2 KB rows)", 1: "lane-group kernel", 2: "TMA kernel"}[args.spmm_impl]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "kernels": kern, "clocks": clocks,
         }
@@ -368,6 +371,7 @@ def main():
     ap.add_argument("--p-local", type=float, default=0.95, help="fraction of sources inside the owner's range (N>1)")
     ap.add_argument("--cpu-nodes", type=int, default=250_000)
     ap.add_argument("--cpu-edges", type=int, default=2_500_000)
+    ap.add_argument("--spmm-impl", type=int, default=0, help="0 auto, 1 lane-group kernel, 2 TMA kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,

@@ -51,6 +51,9 @@ enum {
 const char* b200mp_version(void);
 const char* b200mp_last_error(void);          /* thread-local, human readable */
 int b200mp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+/* Runtime switches for measurements.  "spmm_impl": 0 = auto (default), 1 = lane-group-per-row
+ * kernel only, 2 = persistent TMA-fed kernel wherever it is legal. */
+int b200mp_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------ graph structure (integer work, bit-exact)
  * Replaces: utils/_degree.py:9-31 (degree), index.py:27-37 (ptr2index / index2ptr ==

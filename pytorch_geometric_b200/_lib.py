@@ -21,6 +21,7 @@ _SIGS = {
     "b200mp_version": (ctypes.c_char_p, []),
     "b200mp_last_error": (ctypes.c_char_p, []),
     "b200mp_device_info": (_INT, [_P, _P, _P, _P]),
+    "b200mp_set_option": (_INT, [ctypes.c_char_p, _INT]),
     "b200mp_degree": (_INT, [_P, _I64, _I64, _P, _INT, _P]),
     "b200mp_index2ptr": (_INT, [_P, _I64, _I64, _P, _INT, _P]),
     "b200mp_ptr2index": (_INT, [_P, _I64, _I64, _P, _INT, _P]),

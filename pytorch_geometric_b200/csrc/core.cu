@@ -1,5 +1,6 @@
 // core.cu -- version, error string, device info.
 #include <cstdarg>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -37,4 +38,48 @@ extern "C" int b200mp_device_info(int* sm_count, int* cc_major, int* cc_minor, i
         *l2_bytes = v;
     }
     return B200MP_OK;
+}
+
+// ---------------------------------------------------------------- runtime options
+namespace b200mp {
+static int g_spmm_impl = 0;
+int get_option_spmm_impl() { return g_spmm_impl; }
+
+// Work counters of the persistent kernels: a small device-resident pool, one slot per launch in
+// round-robin order, zeroed on the launching stream right before the kernel (so concurrent
+// launches on different streams never share a slot unless > kSlots launches are in flight).
+constexpr int kSlots = 1024;
+constexpr int kMaxDev = 16;
+static unsigned long long* g_pool[kMaxDev] = {nullptr};
+static unsigned int g_next = 0;
+unsigned long long* tma_counter_slot(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) {
+        set_error("tma_counter_slot: bad device");
+        return nullptr;
+    }
+    if (!g_pool[dev]) {
+        if (cudaMalloc(&g_pool[dev], sizeof(unsigned long long) * kSlots) != cudaSuccess) {
+            set_error("tma_counter_slot: cudaMalloc failed");
+            return nullptr;
+        }
+    }
+    unsigned long long* slot = g_pool[dev] + (__atomic_fetch_add(&g_next, 1u, __ATOMIC_RELAXED) % kSlots);
+    if (cudaMemsetAsync(slot, 0, sizeof(unsigned long long), stream) != cudaSuccess) {
+        set_error("tma_counter_slot: memset failed");
+        return nullptr;
+    }
+    return slot;
+}
+}  // namespace b200mp
+
+extern "C" int b200mp_set_option(const char* name, int value) {
+    if (!name) return B200MP_ERR_INVALID_ARG;
+    if (strcmp(name, "spmm_impl") == 0) {
+        if (value < 0 || value > 2) return B200MP_ERR_INVALID_ARG;
+        b200mp::g_spmm_impl = value;
+        return B200MP_OK;
+    }
+    b200mp::set_error("unknown option %s", name);
+    return B200MP_ERR_INVALID_ARG;
 }

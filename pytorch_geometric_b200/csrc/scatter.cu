@@ -12,11 +12,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
-    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    if (__float_as_int(v) >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));  // sign bit clear (-0.0 goes the other way)
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 __device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
-    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    if (__float_as_int(v) >= 0) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
     else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 __device__ __forceinline__ void atomic_mul_f32(float* addr, float v) {

@@ -1,5 +1,5 @@
 // segment.cu -- C ABI for the segmented reduce without gather (b200mp_segment_csr).
-#include "csr_reduce.cuh"
+#include "csr_dispatch.cuh"
 
 using namespace b200mp;
 
@@ -8,7 +8,7 @@ template <typename T, typename I>
 int segment_typed(const void* ptr, const void* src, void* out, int64_t n_rows, int64_t feat, int reduce,
                   cudaStream_t stream) {
     LongRowPlan plan{nullptr, nullptr, 0, 0, 0, nullptr};
-    return csr_reduce_by_op<T, I, false>(static_cast<const I*>(ptr), static_cast<const I*>(nullptr), nullptr,
+    return csr_reduce_auto<T, I, false>(static_cast<const I*>(ptr), static_cast<const I*>(nullptr), nullptr,
                                          static_cast<const T*>(src), static_cast<T*>(out), n_rows, feat,
                                          reduce, true, plan, nullptr, stream);
 }

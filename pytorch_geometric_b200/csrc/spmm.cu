@@ -1,6 +1,6 @@
 // spmm.cu -- C ABI for the gather + segmented-reduce path (b200mp_spmm_csr) and its backward
 // helpers (min/max tie counting, SDDMM for the edge-weight gradient).
-#include "csr_reduce.cuh"
+#include "csr_dispatch.cuh"
 
 namespace b200mp {
 
@@ -105,7 +105,7 @@ template <typename T, typename I>
 int spmm_typed(const void* rowptr, const void* col, const float* val, const void* x, void* out,
                int64_t n_rows, int64_t feat, int reduce, LongRowPlan plan, const float* bias,
                cudaStream_t stream) {
-    return csr_reduce_by_op<T, I, true>(static_cast<const I*>(rowptr), static_cast<const I*>(col), val,
+    return csr_reduce_auto<T, I, true>(static_cast<const I*>(rowptr), static_cast<const I*>(col), val,
                                         static_cast<const T*>(x), static_cast<T*>(out), n_rows, feat,
                                         reduce, false, plan, bias, stream);
 }

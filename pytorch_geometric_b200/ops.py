@@ -403,3 +403,8 @@ def device_info() -> dict:
     sm, ma, mi, l2 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
     check(lib().b200mp_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(l2)))
     return {"sm_count": sm.value, "cc": (ma.value, mi.value), "l2_bytes": l2.value}
+
+
+def set_option(name: str, value: int) -> None:
+    """Runtime switches of the library (b200mp_set_option), e.g. set_option("spmm_impl", 1)."""
+    check(lib().b200mp_set_option(name.encode(), int(value)), "set_option")

@@ -133,9 +133,13 @@ def test_aggregate_vs_oracle(feat, reduce):
             scale = sum_scale(x, src, dst, weights, N) if reduce in ("sum", "mean") else np.abs(ref)
             err = np.abs(out - ref)
             assert (err <= RTOL * scale + 1e-30).all(), f"max rel err {np.max(err / (scale + 1e-30)):.2e}"
-            if reduce in ("min", "max") or (chunk == 512 and feat % 4 == 0 and feat >= 4):
-                # single lane group per row, CSR order == the reference's edge order: bit-identical
+            if reduce in ("min", "max"):
                 assert np.array_equal(out, ref)
+            elif feat % 4 == 0:
+                # rows walked by a single lane group (deg <= chunk): CSR order == the reference's edge
+                # order and products are rounded before the add => bit-identical to the CPU reference
+                short = O.degree(dst, N) <= chunk
+                assert np.array_equal(out[short], ref[short])
 
 
 @pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
@@ -169,9 +173,12 @@ def test_aggregate_weight_grad_vs_oracle():
     out.backward(cu(gout))
     oout = O.gather_scatter(x, src, dst, w, N, "sum")
     gx, gw = O.gather_scatter_backward(gout, x, oout, src, dst, w, "sum", need_grad_w=True)
-    assert_close(npy(out), oout, rtol=1e-5, atol=1e-5)
-    assert_close(npy(xt.grad), gx, rtol=1e-5, atol=1e-4)
-    assert_close(npy(wt.grad), gw, rtol=1e-5, atol=1e-4)
+    # relative to the sum of |terms| (hub rows are summed chunk-wise, i.e. in a different order)
+    assert (np.abs(npy(out) - oout) <= RTOL * sum_scale(x, src, dst, w, N) + 1e-30).all()
+    gscale = O.gather_scatter(np.abs(gout), dst, src, np.abs(w), N, "sum") + 1e-30
+    assert (np.abs(npy(xt.grad) - gx) <= RTOL * gscale).all()
+    wscale = (np.abs(gout[dst]) * np.abs(x[src])).sum(1) + 1e-30
+    assert (np.abs(npy(wt.grad) - gw) <= 1e-5 * wscale).all()
 
 
 @pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
