@@ -215,6 +215,7 @@ def run_b200(args):
 
     N, E, F = args.nodes, args.edges, args.feat
     ops.set_option("spmm_impl", args.spmm_impl)
+    ops.set_option("spmm_tune", args.spmm_tune)
     torch.manual_seed(1234 + rank)
     conv = GCNConv(F, F, cached=True).to(dev)
     with torch.no_grad():
@@ -372,6 +373,7 @@ def main():
     ap.add_argument("--cpu-nodes", type=int, default=250_000)
     ap.add_argument("--cpu-edges", type=int, default=2_500_000)
     ap.add_argument("--spmm-impl", type=int, default=0, help="0 auto, 1 lane-group kernel, 2 TMA kernel")
+    ap.add_argument("--spmm-tune", type=int, default=0, help="tuning variant of the lane-group kernel (csr_reduce.cuh)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,

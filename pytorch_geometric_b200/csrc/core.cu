@@ -44,6 +44,8 @@ extern "C" int b200mp_device_info(int* sm_count, int* cc_major, int* cc_minor, i
 namespace b200mp {
 static int g_spmm_impl = 0;
 int get_option_spmm_impl() { return g_spmm_impl; }
+static int g_spmm_tune = 0;
+int get_option_spmm_tune() { return g_spmm_tune; }
 
 // Work counters of the persistent kernels: a small device-resident pool, one slot per launch in
 // round-robin order, zeroed on the launching stream right before the kernel (so concurrent
@@ -78,6 +80,10 @@ extern "C" int b200mp_set_option(const char* name, int value) {
     if (strcmp(name, "spmm_impl") == 0) {
         if (value < 0 || value > 2) return B200MP_ERR_INVALID_ARG;
         b200mp::g_spmm_impl = value;
+        return B200MP_OK;
+    }
+    if (strcmp(name, "spmm_tune") == 0) {
+        b200mp::g_spmm_tune = value;
         return B200MP_OK;
     }
     b200mp::set_error("unknown option %s", name);

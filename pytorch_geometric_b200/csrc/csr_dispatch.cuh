@@ -19,8 +19,12 @@ int csr_reduce_variant(const I* rowptr, const I* col, const float* val, const T*
     const size_t row_bytes = static_cast<size_t>(feat) * sizeof(T);
     const bool tma_ok = row_bytes % 16 == 0 && row_bytes >= 512 && row_bytes <= 2048 && aligned16(x) &&
                         aligned16(out) && (plan.n_chunks == 0 || aligned16(plan.partials));
+    // Measured on B200 (profiles/r1_spmm_tuning.md): the lane-group kernel at 48 warps/SM reaches
+    // 7.1 TB/s of algorithmic bytes on the headline shape, the TMA-fed kernel 3.5 TB/s (it is
+    // issue-bound at 6 warps/SM) -- so "auto" is the lane-group kernel; the TMA variant stays
+    // selectable for the A/B evidence and further tuning.
     const int impl = get_option_spmm_impl();
-    if (tma_ok && impl != 1)
+    if (tma_ok && impl == 2)
         return csr_tma_launch<T, I, RED, GATHER>(rowptr, col, val, x, out, n_rows, feat, is_mean, inf_to_zero, plan,
                                                  bias, stream);
     return csr_reduce_dispatch<T, I, RED, GATHER>(rowptr, col, val, x, out, n_rows, feat, is_mean, inf_to_zero, plan,

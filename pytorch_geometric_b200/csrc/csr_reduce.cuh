@@ -22,6 +22,8 @@
 
 namespace b200mp {
 
+int get_option_spmm_tune();  // b200mp_set_option("spmm_tune", k): see launch_vec
+
 struct LongRowPlan {
     const int64_t* long_rows;   // [n_long]
     const int64_t* chunk_ptr;   // [n_long + 1]
@@ -72,14 +74,17 @@ __device__ __forceinline__ float finalize(float acc, int64_t deg, bool is_mean, 
     return acc;
 }
 
-template <typename T, typename I, int G, int VPL, int RED, bool GATHER>
-__global__ void __launch_bounds__(256)
+// UNR_OVR / BLOCK / MINB are tuning knobs (independent row loads in flight per lane, CTA size,
+// minimum resident CTAs per SM => register cap); the defaults are the measured best (profiles/).
+template <typename T, typename I, int G, int VPL, int RED, bool GATHER, int UNR_OVR = 0, int BLOCK = 256,
+          int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB)
 csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
                   const float* __restrict__ val, const T* __restrict__ x, T* __restrict__ out,
                   int64_t n_rows, int n_vec, bool is_mean, bool inf_to_zero, LongRowPlan plan,
                   const float* __restrict__ bias) {
     constexpr int EPV = ElemTraits<T>::kPerVec;
-    constexpr int UNR = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2);
+    constexpr int UNR = UNR_OVR ? UNR_OVR : (VPL == 1 ? 8 : (VPL == 2 ? 4 : 2));
     const int lig = threadIdx.x & (G - 1);                     // lane in group
     const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     int64_t row, begin, end;
@@ -271,11 +276,34 @@ inline void launch_vec(const I* rowptr, const I* col, const float* val, const T*
                        int64_t n_rows, int n_vec, bool is_mean, bool inf_to_zero,
                        const LongRowPlan& plan, const float* bias, cudaStream_t stream) {
     const int64_t items = plan.n_chunks + n_rows;
-    const int64_t groups_per_block = 256 / G;
-    const int64_t blocks = ceil_div(items, groups_per_block);
-    if (blocks == 0) return;
-    csr_reduce_kernel<T, I, G, VPL, RED, GATHER><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-        rowptr, col, val, x, out, n_rows, n_vec, is_mean, inf_to_zero, plan, bias);
+    if (items == 0) return;
+#define B200MP_LAUNCH_TUNED(UNR_, BLOCK_, MINB_)                                                           \
+    csr_reduce_kernel<T, I, G, VPL, RED, GATHER, UNR_, BLOCK_, MINB_>                                      \
+        <<<static_cast<unsigned>(ceil_div(items, BLOCK_ / G)), BLOCK_, 0, stream>>>(                       \
+            rowptr, col, val, x, out, n_rows, n_vec, is_mean, inf_to_zero, plan, bias)
+    if (G == 32 && VPL == 2 && RED == B200MP_SUM && GATHER) {
+        // the headline shape (F = 256 fp32 / 512 bf16): tuning variants selectable at run time
+        switch (get_option_spmm_tune()) {
+            case 1: B200MP_LAUNCH_TUNED(4, 256, 4); return;     // <= 64 regs, 32 warps / SM
+            case 2: B200MP_LAUNCH_TUNED(8, 256, 2); return;     // 16 row loads in flight per lane
+            case 3: B200MP_LAUNCH_TUNED(4, 128, 8); return;     // small CTAs, <= 64 regs
+            case 4: B200MP_LAUNCH_TUNED(2, 256, 6); return;     // <= 40 regs, 48 warps / SM
+            case 5: B200MP_LAUNCH_TUNED(8, 128, 4); return;     // small CTAs, 16 loads in flight
+            case 6: B200MP_LAUNCH_TUNED(2, 128, 12); return;    // <= 40 regs, small CTAs
+            case 7: B200MP_LAUNCH_TUNED(1, 256, 8); return;     // <= 32 regs, 64 warps / SM
+            case 8: B200MP_LAUNCH_TUNED(2, 256, 8); return;     // <= 32 regs, 64 warps / SM
+            case 9: B200MP_LAUNCH_TUNED(3, 256, 6); return;     // <= 40 regs, 6 loads in flight
+            case 10: B200MP_LAUNCH_TUNED(2, 512, 3); return;    // <= 40 regs, large CTAs
+            default: break;
+        }
+    }
+    // Default = the measured best of the sweep in profiles/r1_spmm_tuning.md: occupancy beats
+    // per-lane memory parallelism -- 4 sixteen-byte row loads in flight per lane, 128-thread CTAs,
+    // registers capped at 40 (fp32) / 64 (bf16: twice the accumulators) => 48 / 32 warps per SM.
+    constexpr int kUnr = VPL >= 4 ? 1 : 4 / VPL;
+    if (sizeof(T) == 4) B200MP_LAUNCH_TUNED(kUnr, 128, 12);
+    else B200MP_LAUNCH_TUNED(kUnr, 128, 8);
+#undef B200MP_LAUNCH_TUNED
 }
 
 template <typename T, typename I, int RED, bool GATHER>
