@@ -247,6 +247,9 @@ def run_b200(args):
         conv.bias.grad = None
         out = fwd(x)
         out.backward(gout)
+        if world > 1:                       # data-parallel weight gradients, as DDP would do
+            dist.all_reduce(conv.lin.weight.grad)
+            dist.all_reduce(conv.bias.grad)
         return out
 
     def sync_all():

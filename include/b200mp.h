@@ -134,12 +134,16 @@ int b200mp_csr_plan_fill(const void* rowptr, int64_t n_rows, int64_t chunk, int6
  * Long rows: pass the plan (long_rows, chunk_ptr, n_long_rows, n_chunks, chunk) and a partials
  * workspace of n_chunks * feat fp32, or n_long_rows = 0 to walk every row with one lane group.
  * bias (nullable, feat fp32) is added to every output row in the epilogue (GCNConv's `out + bias`,
- * gcn_conv.py:265-266, without a second pass over [N, F]). */
+ * gcn_conv.py:265-266, without a second pass over [N, F]).
+ * x_halo (nullable): second source segment for node-sharded runs -- column ids >= n_local_cols
+ * are read from x_halo[c - n_local_cols, :] (the rows received by the halo all_to_all) so local
+ * and remote rows are never concatenated (n_cols = n_local_cols + #halo rows). */
 int b200mp_spmm_csr(const void* rowptr, const void* col, const float* val, const void* x,
                     void* out, int64_t n_rows, int64_t n_cols, int64_t feat, int reduce,
                     const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
                     int64_t n_chunks, int64_t chunk, float* partials, const float* bias,
-                    int idx_dtype, int val_dtype, void* stream);
+                    const void* x_halo, int64_t n_local_cols, int idx_dtype, int val_dtype,
+                    void* stream);
 
 /* Segmented reduce without gather: out[i,:] = REDUCE_{e in [ptr[i], ptr[i+1])} src[e,:].
  * Replaces utils/_segment.py:11-50 (torch._segment_reduce / torch_scatter.segment_csr) and the
@@ -175,6 +179,10 @@ int b200mp_sddmm_csr(const void* rowptr, const void* col, const void* a, const v
 int b200mp_scatter_coo(const float* src, const void* index, float* out, float* count,
                        int64_t n_src, int64_t n_rows, int64_t feat, int reduce, int idx_dtype,
                        void* stream);
+/* out[index[e], :] += src[e, :] into an EXISTING fp32 out (no initialisation; atomics): the
+ * return leg of the multi-GPU halo exchange (aten::index_add_). */
+int b200mp_index_add_rows(const float* src, const void* index, float* out, int64_t n_src,
+                          int64_t feat, int idx_dtype, void* stream);
 /* Gather rows: out[e,:] = x[index[e],:]  (aten::index_select, message_passing.py:263-290) --
  * only used by the unfused compatibility path and by backward of scatter. scale (nullable, one
  * fp32 per row of out) multiplies each gathered row. */

@@ -31,6 +31,10 @@ struct LongRowPlan {
     int64_t n_chunks;
     int64_t chunk;              // edges per chunk
     float* partials;            // [n_chunks, feat] fp32
+    // optional second source segment (multi-GPU halo rows): column ids >= split are read from
+    // x2[(c - split), :] instead of x[c, :], so local and received rows never need concatenating
+    const void* x2;
+    int64_t split;
 };
 
 // Decode a work item into (row, begin, end, is_chunk).  Items [0, n_chunks) are chunks of long
@@ -94,6 +98,8 @@ csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
     if (G == 32 && !active) return;         // warp-uniform
     const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
     const char* xb = reinterpret_cast<const char*>(x);
+    const char* xb2 = plan.x2 ? reinterpret_cast<const char*>(plan.x2) - static_cast<size_t>(plan.split) * row_bytes : xb;
+    const int64_t split = plan.x2 ? plan.split : INT64_MAX;
 
     for (int vbase = 0; vbase < n_vec; vbase += G * VPL) {   // one trip unless feat is huge
         float acc[VPL][EPV];
@@ -123,7 +129,7 @@ csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
                         const int64_t c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);
                         w[u] = __shfl_sync(0xffffffffu, w_l, (j + u) & 31);
                         if (j + u < n) {
-                            const char* p = xb + static_cast<size_t>(c) * row_bytes + voff;
+                            const char* p = (c < split ? xb : xb2) + static_cast<size_t>(c) * row_bytes + voff;
 #pragma unroll
                             for (int k = 0; k < VPL; ++k)
                                 if (vvalid[k]) buf[u][k] = ldg_row16(p + static_cast<size_t>(k) * G * 16);
@@ -158,7 +164,7 @@ csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
                     if (e + u < end) {
                         const int64_t c = GATHER ? static_cast<int64_t>(ldg_idx(col + e + u)) : (e + u);
                         if (val) w[u] = __ldg(val + e + u);
-                        if (vvalid[0]) buf[u][0] = ldg_row16(xb + static_cast<size_t>(c) * row_bytes + voff);
+                        if (vvalid[0]) buf[u][0] = ldg_row16((c < split ? xb : xb2) + static_cast<size_t>(c) * row_bytes + voff);
                     }
                 }
 #pragma unroll
@@ -253,7 +259,9 @@ csr_reduce_scalar_kernel(const I* __restrict__ rowptr, const I* __restrict__ col
                 if (e + u < end) {
                     const int64_t c = GATHER ? static_cast<int64_t>(ldg_idx(col + e + u)) : (e + u);
                     if (val) w[u] = __ldg(val + e + u);
-                    v[u] = ElemTraits<T>::to_float(x[c * feat + f]);
+                    v[u] = ElemTraits<T>::to_float((plan.x2 && c >= plan.split)
+                                                       ? static_cast<const T*>(plan.x2)[(c - plan.split) * feat + f]
+                                                       : x[c * feat + f]);
                 }
             }
 #pragma unroll

@@ -86,6 +86,8 @@ csr_tma_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const fl
     uint32_t phases = 0;                        // bit k: parity to wait for on slot k (warp-uniform)
 
     const char* xb = reinterpret_cast<const char*>(x);
+    const char* xb2 = plan.x2 ? reinterpret_cast<const char*>(plan.x2) - static_cast<size_t>(plan.split) * row_bytes : xb;
+    const int64_t split = plan.x2 ? plan.split : INT64_MAX;
     const int64_t n_blocks = (n_rows + kTmaUnitRows - 1) / kTmaUnitRows;
     const int64_t n_units = plan.n_chunks + n_blocks;
     bool vvalid[VPL];
@@ -143,7 +145,7 @@ csr_tma_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const fl
             c_next = GATHER ? static_cast<int64_t>(ldg_idx(col + e_begin + lane)) : (e_begin + lane);
             if (val) w_next = __ldg(val + e_begin + lane);
             mbar_expect_tx(bars + lane * 8u, row_bytes);
-            tma_load_row(ring + lane * row_bytes, xb + static_cast<size_t>(c_next) * row_bytes, row_bytes, bars + lane * 8u);
+            tma_load_row(ring + lane * row_bytes, (c_next < split ? xb : xb2) + static_cast<size_t>(c_next) * row_bytes, row_bytes, bars + lane * 8u);
         }
         for (int64_t e0 = e_begin; e0 < e_end; e0 += kTmaSlots) {
             const int n = static_cast<int>(e_end - e0 < kTmaSlots ? e_end - e0 : kTmaSlots);
@@ -190,7 +192,7 @@ csr_tma_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const fl
                     __syncwarp();
                     if (lane >= q0 && lane < q1 && have_next) {
                         mbar_expect_tx(bars + lane * 8u, row_bytes);
-                        tma_load_row(ring + lane * row_bytes, xb + static_cast<size_t>(c_next) * row_bytes, row_bytes,
+                        tma_load_row(ring + lane * row_bytes, (c_next < split ? xb : xb2) + static_cast<size_t>(c_next) * row_bytes, row_bytes,
                                      bars + lane * 8u);
                     }
                 }

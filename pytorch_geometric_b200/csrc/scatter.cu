@@ -192,6 +192,29 @@ extern "C" int b200mp_scatter_coo(const float* src, const void* index, float* ou
     return B200MP_ERR_UNSUPPORTED;
 }
 
+// out[index[e], :] += src[e, :] into an EXISTING out (no initialisation): the return leg of the
+// halo exchange (gradient rows of remote sources added into their owner's rows).
+extern "C" int b200mp_index_add_rows(const float* src, const void* index, float* out, int64_t n_src, int64_t feat,
+                                     int idx_dtype, void* stream) {
+    B200MP_CHECK_ARG(n_src >= 0 && feat >= 0);
+    if (n_src == 0 || feat == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(src && index && out);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool v4 = feat % 4 == 0 && aligned16(src) && aligned16(out);
+    if (idx_dtype == B200MP_I32) {
+        if (v4) scatter_add_v4_kernel<int32_t><<<blocks_for(n_src * (feat / 4)), kT, 0, s>>>(src, static_cast<const int32_t*>(index), out, nullptr, n_src, static_cast<int>(feat / 4));
+        else scatter_scalar_kernel<int32_t, B200MP_SUM><<<blocks_for(n_src * feat), kT, 0, s>>>(src, static_cast<const int32_t*>(index), out, nullptr, n_src, feat);
+    } else if (idx_dtype == B200MP_I64) {
+        if (v4) scatter_add_v4_kernel<int64_t><<<blocks_for(n_src * (feat / 4)), kT, 0, s>>>(src, static_cast<const int64_t*>(index), out, nullptr, n_src, static_cast<int>(feat / 4));
+        else scatter_scalar_kernel<int64_t, B200MP_SUM><<<blocks_for(n_src * feat), kT, 0, s>>>(src, static_cast<const int64_t*>(index), out, nullptr, n_src, feat);
+    } else {
+        set_error("bad idx_dtype %d", idx_dtype);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    B200MP_LAUNCH_CHECK();
+    return B200MP_OK;
+}
+
 extern "C" int b200mp_gather_rows(const void* x, const void* index, const float* scale, void* out, int64_t n_out,
                                   int64_t feat, int idx_dtype, int val_dtype, void* stream) {
     B200MP_CHECK_ARG(n_out >= 0 && feat >= 0);

@@ -246,7 +246,7 @@ class LongRowPlan:
 # ------------------------------------------------------------------ the hot path
 def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_rows: int, reduce: str = "sum",
              plan: Optional[LongRowPlan] = None, out: Optional[Tensor] = None,
-             bias: Optional[Tensor] = None) -> Tensor:
+             bias: Optional[Tensor] = None, x_halo: Optional[Tensor] = None) -> Tensor:
     """out[i,:] = REDUCE_{e in row i} val[e] * x[col[e],:] (+ bias)  (x: [n_cols, F] contiguous)."""
     _cuda(rowptr, col, val, x)
     if x.dim() != 2:
@@ -269,8 +269,14 @@ def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_ro
             bias = bias.detach().float().contiguous()
         if bias.numel() != F:
             raise ValueError("bias must have one entry per feature")
+    n_cols, n_local = x.size(0), 0
+    if x_halo is not None:
+        _cuda(x_halo)
+        if x_halo.dtype != x.dtype or x_halo.dim() != 2 or x_halo.size(1) != F or not x_halo.is_contiguous():
+            raise ValueError("x_halo must be a contiguous [n_halo, F] tensor of x's dtype")
+        n_local, n_cols = x.size(0), x.size(0) + x_halo.size(0)
     _timed("spmm_csr", 2 if args[2] else 1, lib().b200mp_spmm_csr, _p(rowptr), _p(col), _p(val), _p(x), _p(out),
-           n_rows, x.size(0), F, REDUCE[reduce], *args, _p(bias), it, _vdt(x), _stream())
+           n_rows, n_cols, F, REDUCE[reduce], *args, _p(bias), _p(x_halo), n_local, it, _vdt(x), _stream())
     return out
 
 
@@ -329,6 +335,17 @@ def scatter_coo(src: Tensor, index: Tensor, n_rows: int, reduce: str = "sum") ->
     check(lib().b200mp_scatter_coo(_p(flat), _p(index), _p(out), _p(count), flat.size(0), n_rows, flat.size(1),
                                    REDUCE[reduce], _idt(index), _stream()), "scatter_coo")
     return out.view((n_rows, ) + tuple(src.shape[1:]))
+
+
+def index_add_rows(out: Tensor, index: Tensor, src: Tensor) -> Tensor:
+    """out[index[e], :] += src[e, :] in place (fp32, atomics)."""
+    _cuda(out, index, src)
+    if out.dtype != torch.float32 or src.dtype != torch.float32 or not out.is_contiguous():
+        raise TypeError("index_add_rows works on contiguous fp32 tensors")
+    src, index = src.contiguous(), index.contiguous()
+    check(lib().b200mp_index_add_rows(_p(src), _p(index), _p(out), index.numel(), out.size(1), _idt(index),
+                                      _stream()), "index_add_rows")
+    return out
 
 
 def gather_rows(x: Tensor, index: Tensor, scale: Optional[Tensor] = None) -> Tensor:
