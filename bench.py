@@ -157,14 +157,14 @@ def run_reference(args):
     value = E / dt
     cores = torch.get_num_threads()
     sample = f"GCNConv({F},{F}) fwd+bwd, N={N}, E={E} power-law, fp32, COO gather->mul->scatter_add_ (reference default path), {steps} steps"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "edges/sec (GCNConv fwd+bwd)", "value": value, "unit": "edges/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": sample, "host_cpus": os.cpu_count(), "torch_threads": cores},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def cpu_baseline_quick(args):
@@ -358,12 +358,26 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "kernels": kern, "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Exactly ONE JSON line on the real stdout (libraries such as NCCL print banners to fd 1,
+    so fd 1 is pointed at stderr for the whole run and the result goes to the saved descriptor)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

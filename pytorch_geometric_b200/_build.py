@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
+OBJ = os.environ.get("B200MP_OBJ_DIR", os.path.join("/tmp", f"b200mp_build_{os.getuid()}"))  # objects stay out of tree
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200mp.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")

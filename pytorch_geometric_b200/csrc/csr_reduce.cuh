@@ -292,16 +292,10 @@ inline void launch_vec(const I* rowptr, const I* col, const float* val, const T*
     if (G == 32 && VPL == 2 && RED == B200MP_SUM && GATHER) {
         // the headline shape (F = 256 fp32 / 512 bf16): tuning variants selectable at run time
         switch (get_option_spmm_tune()) {
-            case 1: B200MP_LAUNCH_TUNED(4, 256, 4); return;     // <= 64 regs, 32 warps / SM
-            case 2: B200MP_LAUNCH_TUNED(8, 256, 2); return;     // 16 row loads in flight per lane
-            case 3: B200MP_LAUNCH_TUNED(4, 128, 8); return;     // small CTAs, <= 64 regs
-            case 4: B200MP_LAUNCH_TUNED(2, 256, 6); return;     // <= 40 regs, 48 warps / SM
-            case 5: B200MP_LAUNCH_TUNED(8, 128, 4); return;     // small CTAs, 16 loads in flight
-            case 6: B200MP_LAUNCH_TUNED(2, 128, 12); return;    // <= 40 regs, small CTAs
-            case 7: B200MP_LAUNCH_TUNED(1, 256, 8); return;     // <= 32 regs, 64 warps / SM
-            case 8: B200MP_LAUNCH_TUNED(2, 256, 8); return;     // <= 32 regs, 64 warps / SM
-            case 9: B200MP_LAUNCH_TUNED(3, 256, 6); return;     // <= 40 regs, 6 loads in flight
-            case 10: B200MP_LAUNCH_TUNED(2, 512, 3); return;    // <= 40 regs, large CTAs
+            // (the full 11-point sweep and its numbers are in profiles/r1_spmm_tuning.md)
+            case 1: B200MP_LAUNCH_TUNED(4, 256, 1); return;     // unconstrained registers (86): 16 warps / SM
+            case 2: B200MP_LAUNCH_TUNED(4, 256, 4); return;     // <= 64 regs, 32 warps / SM
+            case 3: B200MP_LAUNCH_TUNED(1, 256, 8); return;     // <= 32 regs, 64 warps / SM, 2 loads in flight
             default: break;
         }
     }

@@ -1,0 +1,63 @@
+"""The reference-side binding (pytorch_geometric_b200/install.py), checked in the build container
+where the reference is importable from /root/reference.  On the GPU box the reference does not
+exist, so these tests skip there (nothing at run time may read /root/reference on that box)."""
+import os
+import sys
+
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "torch_geometric")),
+                                reason="the reference is only importable in the build container")
+
+
+@pytest.fixture
+def tg():
+    sys.path.insert(0, REF)
+    try:
+        import torch_geometric
+        yield torch_geometric
+    finally:
+        sys.path.remove(REF)
+
+
+def test_install_rebinds_consumers_and_cpu_falls_through(tg):
+    import torch_geometric.nn.aggr.base as aggr_base
+    import torch_geometric.nn.conv.gcn_conv as gcn_conv
+    from torch_geometric.utils import _scatter
+
+    import pytorch_geometric_b200.install as b200
+
+    orig = _scatter.scatter
+    src = torch.randn(10, 4)
+    index = torch.tensor([0, 1, 0, 1, 2, 2, 3, 3, 3, 0])
+    before = orig(src, index, 0, 5, "sum")
+    counts = b200.install(layers=False)
+    try:
+        assert counts["scatter"] >= 10 and counts["softmax"] >= 1 and counts["spmm"] >= 1
+        assert _scatter.scatter is not orig and aggr_base.scatter is _scatter.scatter
+        assert gcn_conv.scatter is _scatter.scatter
+        # CPU tensors still run the untouched reference: bit-identical results
+        assert torch.equal(_scatter.scatter(src, index, 0, 5, "sum"), before)
+        conv = tg.nn.GCNConv(4, 3)
+        ei = torch.tensor([[0, 1, 2, 3], [1, 2, 3, 0]])
+        x = torch.randn(4, 4)
+        out1 = conv(x, ei)
+    finally:
+        b200.uninstall()
+    assert _scatter.scatter is orig and aggr_base.scatter is orig
+    assert torch.equal(conv(x, ei), out1)
+
+
+def test_install_layers_swaps_conv_classes(tg):
+    import pytorch_geometric_b200.install as b200
+    from pytorch_geometric_b200 import nn as ours
+
+    orig = tg.nn.GCNConv
+    b200.install(layers=True)
+    try:
+        assert tg.nn.GCNConv is ours.GCNConv and tg.nn.GATConv is ours.GATConv
+    finally:
+        b200.uninstall()
+    assert tg.nn.GCNConv is orig
