@@ -216,6 +216,8 @@ def run_b200(args):
     N, E, F = args.nodes, args.edges, args.feat
     ops.set_option("spmm_impl", args.spmm_impl)
     ops.set_option("spmm_tune", args.spmm_tune)
+    from pytorch_geometric_b200 import dense
+    dense.set_backend(args.dense)
     torch.manual_seed(1234 + rank)
     conv = GCNConv(F, F, cached=True).to(dev)
     with torch.no_grad():
@@ -352,7 +354,8 @@ def run_b200(args):
                        "nodes_per_gpu": N, "edges_per_gpu": E, "feat": F, "layers": 1,
                        "l2_policy": "inputs (x, grad, CSR > 10 GB) are far larger than the 126 MB L2; no explicit flush",
                        "parallelism": "single GPU" if world == 1 else f"node-range sharding x{world}, p_local={args.p_local}, halo all_to_all",
-                       "gemm": "torch.nn.functional.linear (cuBLAS fp32, allow_tf32=False)",
+                       "gemm": ("hand-written tcgen05 3xTF32 (fp32-accurate, csrc/gemm_tf32x3.cu)" if args.dense == "tf32x3"
+                                else "torch.nn.functional.linear (cuBLAS fp32, allow_tf32=False)"),
                        "long_rows": graph.plan.n_long, "chunks": graph.plan.n_chunks,
                        "spmm_impl": {0: "auto (TMA streaming kernel for 512 B..2 KB rows)", 1: "lane-group kernel", 2: "TMA kernel"}[args.spmm_impl]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
@@ -391,6 +394,8 @@ def main():
     ap.add_argument("--cpu-edges", type=int, default=2_500_000)
     ap.add_argument("--spmm-impl", type=int, default=0, help="0 auto, 1 lane-group kernel, 2 TMA kernel")
     ap.add_argument("--spmm-tune", type=int, default=0, help="tuning variant of the lane-group kernel (csr_reduce.cuh)")
+    ap.add_argument("--dense", default="tf32x3", choices=["tf32x3", "cublas"],
+                    help="dense transform: hand-written tcgen05 3xTF32 GEMM (fp32-accurate) or strict-fp32 cuBLAS")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,

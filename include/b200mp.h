@@ -227,6 +227,26 @@ int b200mp_gat_fused_csr_backward(const void* rowptr, const void* col, const voi
                                   int64_t chan, float slope, int idx_dtype, int val_dtype,
                                   void* stream);
 
+/* ------------------------------------------------------------------ dense transform on tensor cores
+ * fp32-accurate 3xTF32 GEMMs (tcgen05 + TMEM + TMA, csrc/gemm_tf32x3.cu) for the layer's
+ * Linear (nn/dense/linear.py:121-127: F.linear, run by the reference as strict-fp32 cuBLAS):
+ *   b200mp_linear_tf32x3            y [M,N]  = x [M,K] . w[N,K]^T
+ *   b200mp_linear_grad_input_tf32x3 gx[M,K]  = g [M,N] . w[N,K]
+ *   b200mp_linear_grad_weight_tf32x3 gw[N,K] = g [M,N]^T . x[M,K]   (deterministic split-K)
+ * w_hi/w_lo come from b200mp_split_tf32 (w = w_hi + w_lo, w_hi = rn_tf32(w)).  All matrices
+ * row-major, contiguous, 16-byte aligned.  Shape limits (else B200MP_ERR_UNSUPPORTED and the caller
+ * uses a library GEMM): reduction dim % 32 == 0, output width in {64, 128} or a multiple of 256,
+ * and for grad_weight N % 128 == 0. */
+int b200mp_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream);
+int b200mp_linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, float* y, int64_t m,
+                         int64_t n, int64_t k, void* stream);
+int b200mp_linear_grad_input_tf32x3(const float* g, const float* w_hi, const float* w_lo, float* gx,
+                                    int64_t m, int64_t n, int64_t k, void* stream);
+int64_t b200mp_linear_grad_weight_workspace_bytes(int64_t m, int64_t n, int64_t k);
+int b200mp_linear_grad_weight_tf32x3(const float* g, const float* x, float* gw, int64_t m, int64_t n,
+                                     int64_t k, void* workspace, int64_t workspace_bytes,
+                                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,11 @@ _SIGS = {
     "b200mp_minmax_backward": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
     "b200mp_sddmm_csr": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
     "b200mp_scatter_coo": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _INT, _INT, _P]),
+    "b200mp_split_tf32": (_INT, [_P, _P, _P, _I64, _P]),
+    "b200mp_linear_tf32x3": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P]),
+    "b200mp_linear_grad_input_tf32x3": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P]),
+    "b200mp_linear_grad_weight_workspace_bytes": (_I64, [_I64, _I64, _I64]),
+    "b200mp_linear_grad_weight_tf32x3": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _P]),
     "b200mp_index_add_rows": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P]),
     "b200mp_gather_rows": (_INT, [_P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
     "b200mp_softmax_csr": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P]),

@@ -1,0 +1,511 @@
+// gemm_tf32x3.cu -- fp32-accurate dense transform on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// The only GEMM-shaped work on the path is the layer's dense transform:
+//     y  = x  W^T      [M,K] x [N,K]^T        (forward,       nn/dense/linear.py:121-127)
+//     gx = g  W        [M,N] x [N,K]          (grad wrt input)
+//     gW = g^T x       [N,M] x [M,K]          (grad wrt weight, reduction over the M = #nodes rows)
+// The reference runs them as strict-fp32 cuBLAS SIMT kernels (allow_tf32=False); at the headline
+// shape (M = 10 M, N = K = 256) those are 24-32 ms each and dominate the step.  A single-pass TF32
+// GEMM would be 10x faster but only ~1e-3 accurate, so this kernel uses the error-compensated
+// 3xTF32 split:  a = a_hi + a_lo  (a_hi = rn_tf32(a), a_lo = a - a_hi exactly), and
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo      (dropped term a_lo*b_lo ~ 2^-22 |a b|)
+// accumulated in fp32 in TMEM -- fp32-class accuracy at a third of the TF32 tensor rate.
+//
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the raw fp32 operand tiles, 128B swizzle
+//   warps 4-7   splitter: turn each landed tile into (hi in place, lo in a second buffer) -- a
+//               layout-agnostic element-wise pass, then fence.proxy.async + mbarrier arrive
+//   warp 1      MMA issuer: one thread issues 4 k-steps x 3 products of tcgen05.mma.kind::tf32
+//               (M=128, N=BN, K=8) per 32-wide k-block, commits to the stage's "empty" barrier
+//   warps 8-11  epilogue: tcgen05.ld 32x32b.x32 TMEM -> registers -> 128-bit global stores,
+//               double-buffered accumulators (2 x BN TMEM columns) so it overlaps the next tile
+// Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]): tcgen05 takes
+// both for TF32, so all three products read x, g and W exactly as they lie in HBM (no transposes).
+// W is split once into (W_hi, W_lo) by a tiny pre-pass; x and g are split in shared memory.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b200mp {
+
+constexpr int kBM = 128;       // UMMA M
+constexpr int kBK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kAccStages = 2;
+constexpr int kGemmThreads = 384;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t s2u(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float rn_tf32(float a) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+    return __uint_as_float(r);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64).
+//   K-major operand : SWIZZLE_128B (2): rows of 128 B (32 tf32 along K), 8-row atoms of 1024 B
+//                     (TMA CU_TENSOR_MAP_SWIZZLE_128B); LBO = 16 B (unused), SBO = 1024 B.
+//   MN-major operand: 32-bit MN-major data only exist as SWIZZLE_128B_BASE32B (1): 128-byte rows of
+//                     32 MN elements, 4 k-rows per 512-byte atom, 32-byte swizzle granule
+//                     (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); LBO = stride between 32-element
+//                     MN slabs, SBO = 512 B between groups of 4 k-rows.
+template <bool MN>
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t slab_stride_bytes) {
+    const uint32_t lbo = MN ? slab_stride_bytes : 16u;
+    const uint32_t sbo = MN ? 512u : 1024u;
+    const uint64_t layout = MN ? 1ull : 2ull;
+    return static_cast<uint64_t>((addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>((lbo >> 4) & 0x3fffu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46) | (layout << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b format TF32 (2)
+// [7,10)/[10,13), a_major [15], b_major [16] (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
+           (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+struct GemmArgs {
+    float* c;             // output [M, ldc] (or split-K partials [splits, M, ldc])
+    int64_t m;            // rows of the output tile space (A's MN extent)
+    int64_t ldc;
+    int n_tiles_m, n_tiles_n;
+    int k_blocks;         // total 32-wide k-blocks
+    int k_blocks_per_split;
+    int n_splits;
+};
+
+// A_MN / B_MN: operand is MN-major (stored row-major as [K, MN]); B_PRE: B arrives pre-split
+// (two tensor maps: hi, lo) so only A is split in shared memory.
+template <int BN, bool A_MN, bool B_MN, bool B_PRE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_hi,
+                   const __grid_constant__ CUtensorMap tmap_b_lo, GemmArgs args) {
+    constexpr uint32_t kABytes = kBM * 128;                     // 16 KB: 128 rows x 32 fp32 (either major)
+    constexpr uint32_t kBBytes = BN * 128;
+    constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+    constexpr uint32_t kTxBytes = kABytes + (B_PRE ? 2 : 1) * kBBytes;
+    constexpr uint32_t kTmemCols = kAccStages * BN;             // 512 for BN = 256
+    constexpr uint32_t kIdesc = instr_desc(kBM, BN, A_MN, B_MN);
+
+    extern __shared__ __align__(1024) unsigned char gemm_smem[];
+    const uint32_t smem_base = (s2u(gemm_smem) + 1023u) & ~1023u;
+    unsigned char* smem_gen = gemm_smem + (smem_base - s2u(gemm_smem));
+    const uint32_t bars = smem_base + kStages * kStageBytes;
+    // barrier slots (8 B each): full[s], split[s], empty[s], tmem_full[a], tmem_empty[a]
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_split = [&](int s) { return bars + 8u * (kStages + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * kStages + s); };
+    auto bar_tfull = [&](int a) { return bars + 8u * (3 * kStages + a); };
+    auto bar_tempty = [&](int a) { return bars + 8u * (3 * kStages + kAccStages + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * kStages + 2 * kAccStages);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            bar_init(bar_full(s), 1);
+            bar_init(bar_split(s), 128);
+            bar_init(bar_empty(s), 1);
+        }
+        for (int a = 0; a < kAccStages; ++a) {
+            bar_init(bar_tfull(a), 1);
+            bar_init(bar_tempty(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int tiles_per_split = args.n_tiles_m * args.n_tiles_n;
+    const int n_work = tiles_per_split * args.n_splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w / tiles_per_split;
+                const int t = w - split * tiles_per_split;
+                const int m0 = (t / args.n_tiles_n) * kBM;
+                const int n0 = (t % args.n_tiles_n) * BN;
+                const int kb0 = split * args.k_blocks_per_split;
+                const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    bar_wait(bar_empty(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * kStageBytes;
+                    const uint32_t sb_hi = sa + 2 * kABytes;
+                    const uint32_t sb_lo = sb_hi + kBBytes;
+                    bar_expect_tx(bar_full(stage), kTxBytes);
+                    if (A_MN) {
+#pragma unroll
+                        for (int s = 0; s < kBM / 32; ++s) tma_load_2d(sa + s * 4096u, &tmap_a, m0 + 32 * s, kb * kBK, bar_full(stage));
+                    } else {
+                        tma_load_2d(sa, &tmap_a, kb * kBK, m0, bar_full(stage));
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int s = 0; s < BN / 32; ++s) {
+                            tma_load_2d(sb_hi + s * 4096u, &tmap_b_hi, n0 + 32 * s, kb * kBK, bar_full(stage));
+                            if (B_PRE) tma_load_2d(sb_lo + s * 4096u, &tmap_b_lo, n0 + 32 * s, kb * kBK, bar_full(stage));
+                        }
+                    } else {
+                        tma_load_2d(sb_hi, &tmap_b_hi, kb * kBK, n0, bar_full(stage));
+                        if (B_PRE) tma_load_2d(sb_lo, &tmap_b_lo, kb * kBK, n0, bar_full(stage));
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w / tiles_per_split;
+                const int kb0 = split * args.k_blocks_per_split;
+                const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
+                bar_wait(bar_tempty(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + static_cast<uint32_t>(acc * BN);
+                uint32_t accumulate = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    bar_wait(bar_full(stage), phase);      // TMA bytes (incl. the pre-split B tiles) have landed
+                    bar_wait(bar_split(stage), phase);     // hi/lo tiles written and fenced by the splitter
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_base + stage * kStageBytes;
+                    const uint32_t sa_lo = sa_hi + kABytes;
+                    const uint32_t sb_hi = sa_hi + 2 * kABytes;
+                    const uint32_t sb_lo = sb_hi + kBBytes;
+#pragma unroll
+                    for (int j = 0; j < kBK / 8; ++j) {
+                        // K-major: 8 tf32 = 32 B further along the 128-byte swizzle row;
+                        // MN-major: the next group of 8 k-rows = 1024 B further.
+                        const uint32_t ao = A_MN ? j * 1024u : j * 32u;
+                        const uint32_t bo = B_MN ? j * 1024u : j * 32u;
+                        const uint64_t a_hi = smem_desc<A_MN>(sa_hi + ao, 4096);
+                        const uint64_t a_lo = smem_desc<A_MN>(sa_lo + ao, 4096);
+                        const uint64_t b_hi = smem_desc<B_MN>(sb_hi + bo, 4096);
+                        const uint64_t b_lo = smem_desc<B_MN>(sb_lo + bo, 4096);
+                        umma_tf32(d, a_lo, b_hi, kIdesc, accumulate);     // small terms first
+                        umma_tf32(d, a_hi, b_lo, kIdesc, 1u);
+                        umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                        accumulate = 1u;
+                    }
+                    umma_commit(bar_empty(stage));                        // frees the smem stage when the MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(bar_tfull(acc));                              // accumulator complete
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== splitter (128 threads) =====================
+        const int tid = threadIdx.x - 128;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w / tiles_per_split;
+            const int kb0 = split * args.k_blocks_per_split;
+            const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                bar_wait(bar_full(stage), phase);
+                unsigned char* sa = smem_gen + stage * kStageBytes;
+                auto split_buf = [&](unsigned char* hi, unsigned char* lo, int bytes) {
+                    for (int off = tid * 16; off < bytes; off += 128 * 16) {
+                        float4 v = *reinterpret_cast<float4*>(hi + off);
+                        float4 h = make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+                        float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        *reinterpret_cast<float4*>(hi + off) = h;
+                        *reinterpret_cast<float4*>(lo + off) = l;
+                    }
+                };
+                split_buf(sa, sa + kABytes, kABytes);
+                if (!B_PRE) split_buf(sa + 2 * kABytes, sa + 2 * kABytes + kBBytes, kBBytes);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async (MMA) reads
+                bar_arrive(bar_split(stage));
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue (128 threads, TMEM lane quadrant = warp % 4) =====================
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w / tiles_per_split;
+            const int t = w - split * tiles_per_split;
+            const int64_t m0 = static_cast<int64_t>(t / args.n_tiles_n) * kBM;
+            const int n0 = (t % args.n_tiles_n) * BN;
+            bar_wait(bar_tfull(acc), acc_phase);
+            tc_fence_after();
+            const int64_t row = m0 + q * 32 + lane;
+            float* crow = args.c + (static_cast<int64_t>(split) * args.m + row) * args.ldc + n0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c0), r);
+                if (row < args.m) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(crow + c0 + i) =
+                            make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                }
+            }
+            tc_fence_before();
+            bar_arrive(bar_tempty(acc));
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// w -> (rn_tf32(w), w - rn_tf32(w)) for the (small) weight matrix
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = w[i], h = rn_tf32(v);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+// out[i] = sum_s part[s][i], fixed order (deterministic split-K)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int splits) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float acc = 0.0f;
+        for (int s = 0; s < splits; ++s) acc = __fadd_rn(acc, part[static_cast<int64_t>(s) * n + i]);
+        out[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols], zero fill.  box_rows == 32 is
+// the MN-major operand form (32 k-rows x 32 MN elements per box): 128B swizzle with a 32-byte atom;
+// otherwise the K-major form: plain 128B swizzle.
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    const CUtensorMapSwizzle swz = box_rows == 32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return B200MP_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", static_cast<int>(r),
+                  static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld), box_rows);
+        return B200MP_ERR_CUDA;
+    }
+    return B200MP_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool B_PRE>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const GemmArgs& args,
+                       cudaStream_t stream) {
+    constexpr size_t smem = kStages * (2 * kBM * 128 + 2 * BN * 128) + 256 + 1024;
+    auto kfn = gemm_tf32x3_kernel<BN, A_MN, B_MN, B_PRE>;
+    B200MP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int n_work = args.n_tiles_m * args.n_tiles_n * args.n_splits;
+    const int grid = n_work < num_sms() ? n_work : num_sms();
+    kfn<<<grid, kGemmThreads, smem, stream>>>(ta, tbh, tbl, args);
+    B200MP_LAUNCH_CHECK();
+    return B200MP_OK;
+}
+
+static bool ok16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace b200mp
+
+using namespace b200mp;
+
+extern "C" int b200mp_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream) {
+    B200MP_CHECK_ARG(n >= 0);
+    if (n == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(w && w_hi && w_lo);
+    split_tf32_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, w_hi, w_lo, n);
+    B200MP_LAUNCH_CHECK();
+    return B200MP_OK;
+}
+
+// y[M,N] = x[M,K] . w[N,K]^T  with w pre-split.  N in {64,128,256} (or a multiple of 256), K % 32 == 0.
+extern "C" int b200mp_linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, float* y, int64_t m, int64_t n,
+                                    int64_t k, void* stream) {
+    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
+    if (m == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(x && w_hi && w_lo && y && ok16(x) && ok16(w_hi) && ok16(w_lo) && ok16(y));
+    if (k % 32 != 0 || !(n == 64 || n == 128 || n % 256 == 0) || m > 0x7fffffffLL) {
+        set_error("linear_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    const int bn = n >= 256 ? 256 : static_cast<int>(n);
+    CUtensorMap ta, tbh, tbl;
+    int rc;
+    if ((rc = make_map(&ta, x, m, k, k, kBM))) return rc;
+    if ((rc = make_map(&tbh, w_hi, n, k, k, bn))) return rc;
+    if ((rc = make_map(&tbl, w_lo, n, k, k, bn))) return rc;
+    GemmArgs a{y, m, n, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n / bn), static_cast<int>(k / 32), static_cast<int>(k / 32), 1};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (bn == 256) return launch_gemm<256, false, false, true>(ta, tbh, tbl, a, s);
+    if (bn == 128) return launch_gemm<128, false, false, true>(ta, tbh, tbl, a, s);
+    return launch_gemm<64, false, false, true>(ta, tbh, tbl, a, s);
+}
+
+// gx[M,K] = g[M,N] . w[N,K]  (w pre-split, read MN-major exactly as stored).  K in {64,128,256,..}, N % 32 == 0.
+extern "C" int b200mp_linear_grad_input_tf32x3(const float* g, const float* w_hi, const float* w_lo, float* gx, int64_t m,
+                                               int64_t n, int64_t k, void* stream) {
+    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
+    if (m == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(g && w_hi && w_lo && gx && ok16(g) && ok16(w_hi) && ok16(w_lo) && ok16(gx));
+    if (n % 32 != 0 || !(k == 64 || k == 128 || k % 256 == 0) || m > 0x7fffffffLL) {
+        set_error("linear_grad_input_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    const int bn = k >= 256 ? 256 : static_cast<int>(k);          // output width is k
+    CUtensorMap ta, tbh, tbl;
+    int rc;
+    if ((rc = make_map(&ta, g, m, n, n, kBM))) return rc;          // A = g: K-major, reduction dim = n
+    if ((rc = make_map(&tbh, w_hi, n, k, k, 32))) return rc;       // B stored [K' = n rows][N' = k cols]: MN-major, 32x32 boxes
+    if ((rc = make_map(&tbl, w_lo, n, k, k, 32))) return rc;
+    GemmArgs a{gx, m, k, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(k / bn), static_cast<int>(n / 32), static_cast<int>(n / 32), 1};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (bn == 256) return launch_gemm<256, false, true, true>(ta, tbh, tbl, a, s);
+    if (bn == 128) return launch_gemm<128, false, true, true>(ta, tbh, tbl, a, s);
+    return launch_gemm<64, false, true, true>(ta, tbh, tbl, a, s);
+}
+
+extern "C" int64_t b200mp_linear_grad_weight_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+    if (m < 0 || n <= 0 || k <= 0) return B200MP_ERR_INVALID_ARG;
+    return static_cast<int64_t>(num_sms()) * n * k * 4 + 256;
+}
+
+// gw[N,K] = g[M,N]^T . x[M,K]: both operands MN-major as stored, deterministic split-K over the M rows.
+// N % 128 == 0, K in {64,128,256,...}.  workspace from b200mp_linear_grad_weight_workspace_bytes().
+extern "C" int b200mp_linear_grad_weight_tf32x3(const float* g, const float* x, float* gw, int64_t m, int64_t n, int64_t k,
+                                                void* workspace, int64_t workspace_bytes, void* stream) {
+    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (m == 0) {
+        B200MP_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * n * k, s));
+        return B200MP_OK;
+    }
+    B200MP_CHECK_ARG(g && x && gw && workspace && ok16(g) && ok16(x) && ok16(gw) && ok16(workspace));
+    if (n % 128 != 0 || !(k == 64 || k == 128 || k % 256 == 0)) {
+        set_error("linear_grad_weight_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    const int bn = k >= 256 ? 256 : static_cast<int>(k);
+    const int tiles = static_cast<int>((n / kBM) * (k / bn));
+    const int64_t kblocks = ceil_div(m, 32);
+    if (kblocks > 0x7fffffffLL) return B200MP_ERR_UNSUPPORTED;
+    int splits = num_sms() / tiles;
+    if (splits < 1) splits = 1;
+    if (splits > kblocks) splits = static_cast<int>(kblocks);
+    const int kbps = static_cast<int>(ceil_div(kblocks, splits));
+    splits = static_cast<int>(ceil_div(kblocks, kbps));            // every split non-empty
+    if (static_cast<int64_t>(splits) * n * k * 4 > workspace_bytes) {
+        set_error("linear_grad_weight_tf32x3: workspace too small");
+        return B200MP_ERR_WORKSPACE;
+    }
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_map(&ta, g, m, n, n, 32))) return rc;           // A[m'=n-index, k'=row]: stored [K' rows][M' cols]
+    if ((rc = make_map(&tb, x, m, k, k, 32))) return rc;
+    GemmArgs a{static_cast<float*>(workspace), n, k, static_cast<int>(n / kBM), static_cast<int>(k / bn), static_cast<int>(kblocks), kbps, splits};
+    if (bn == 256) rc = launch_gemm<256, true, true, false>(ta, tb, tb, a, s);
+    else if (bn == 128) rc = launch_gemm<128, true, true, false>(ta, tb, tb, a, s);
+    else rc = launch_gemm<64, true, true, false>(ta, tb, tb, a, s);
+    if (rc) return rc;
+    const int64_t total = n * k;
+    splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, s>>>(static_cast<const float*>(workspace), gw, total, splits);
+    B200MP_LAUNCH_CHECK();
+    return B200MP_OK;
+}

@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
+from .. import dense
 from .. import functional as Fn
 from .. import ops
 from .. import utils as U
@@ -45,7 +46,7 @@ class _Lin(torch.nn.Module):
         glorot_(self.weight)
 
     def forward(self, x: Tensor) -> Tensor:
-        return F.linear(x, self.weight.to(x.dtype), None if self.bias is None else self.bias.to(x.dtype))
+        return dense.linear(x, self.weight, self.bias)
 
 
 class _BiasAggregate(torch.autograd.Function):
