@@ -44,6 +44,8 @@ extern "C" int b200mp_device_info(int* sm_count, int* cc_major, int* cc_minor, i
 namespace b200mp {
 static int g_spmm_impl = 0;
 int get_option_spmm_impl() { return g_spmm_impl; }
+static int g_gemm_bk = 32;
+int get_option_gemm_bk() { return g_gemm_bk; }
 static int g_spmm_tune = 0;
 int get_option_spmm_tune() { return g_spmm_tune; }
 
@@ -84,6 +86,11 @@ extern "C" int b200mp_set_option(const char* name, int value) {
     }
     if (strcmp(name, "spmm_tune") == 0) {
         b200mp::g_spmm_tune = value;
+        return B200MP_OK;
+    }
+    if (strcmp(name, "gemm_bk") == 0) {
+        if (value != 16 && value != 32) return B200MP_ERR_INVALID_ARG;
+        b200mp::g_gemm_bk = value;
         return B200MP_OK;
     }
     b200mp::set_error("unknown option %s", name);

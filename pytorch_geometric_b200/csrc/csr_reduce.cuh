@@ -35,6 +35,9 @@ struct LongRowPlan {
     // x2[(c - split), :] instead of x[c, :], so local and received rows never need concatenating
     const void* x2;
     int64_t split;
+    // accumulate != 0: out[i,:] += result for rows that have edges (rows without edges are left
+    // untouched) -- used to add the halo-edge contributions after the local-edge sweep (sum only)
+    int accumulate;
 };
 
 // Decode a work item into (row, begin, end, is_chunk).  Items [0, n_chunks) are chunks of long
@@ -209,6 +212,13 @@ csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
 #pragma unroll
                     for (int i = 0; i < EPV; ++i) f[i] = __fadd_rn(f[i], __ldg(bp + i));
                 }
+                if (plan.accumulate) {
+                    if (deg == 0) continue;
+                    float o[EPV];
+                    ElemTraits<T>::unpack(*reinterpret_cast<const Vec16*>(ob + static_cast<size_t>(vbase + lig + k * G) * 16), o);
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) f[i] = __fadd_rn(o[i], f[i]);
+                }
                 stg_stream16(ob + static_cast<size_t>(vbase + lig + k * G) * 16, ElemTraits<T>::pack(f));
             }
         }
@@ -230,6 +240,7 @@ csr_combine_kernel(const I* __restrict__ rowptr, T* __restrict__ out, int64_t fe
         for (int64_t c = c0; c < c1; ++c) acc = red_combine<RED>(acc, plan.partials[c * feat + f]);
         acc = finalize<RED>(acc, deg, is_mean, inf_to_zero);
         if (bias) acc = __fadd_rn(acc, bias[f]);
+        if (plan.accumulate) acc = __fadd_rn(ElemTraits<T>::to_float(out[row * feat + f]), acc);
         out[row * feat + f] = ElemTraits<T>::from_float(acc);
     }
 }
@@ -273,6 +284,10 @@ csr_reduce_scalar_kernel(const I* __restrict__ rowptr, const I* __restrict__ col
         else {
             acc = finalize<RED>(acc, end - begin, is_mean, inf_to_zero);
             if (bias) acc = __fadd_rn(acc, bias[f]);
+            if (plan.accumulate) {
+                if (end == begin) continue;
+                acc = __fadd_rn(ElemTraits<T>::to_float(out[row * feat + f]), acc);
+            }
             out[row * feat + f] = ElemTraits<T>::from_float(acc);
         }
     }

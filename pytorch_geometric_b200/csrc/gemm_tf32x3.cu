@@ -29,8 +29,8 @@
 namespace b200mp {
 
 constexpr int kBM = 128;       // UMMA M
-constexpr int kBK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int kStages = 2;
+// BK (fp32 elements per k-block) is a template parameter: 32 = one 128-byte swizzle row, 2 smem
+// stages of 96 KB (BN = 256); 16 = 64-byte rows (SWIZZLE_64B for K-major operands), 4 stages of 48 KB.
 constexpr int kAccStages = 2;
 constexpr int kGemmThreads = 384;
 
@@ -110,11 +110,12 @@ __device__ __forceinline__ float rn_tf32(float a) {
 //                     32 MN elements, 4 k-rows per 512-byte atom, 32-byte swizzle granule
 //                     (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); LBO = stride between 32-element
 //                     MN slabs, SBO = 512 B between groups of 4 k-rows.
-template <bool MN>
+//   K-major with BK = 16: SWIZZLE_64B (4): rows of 64 B, 8-row atoms of 512 B.
+template <bool MN, int BK>
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t slab_stride_bytes) {
     const uint32_t lbo = MN ? slab_stride_bytes : 16u;
-    const uint32_t sbo = MN ? 512u : 1024u;
-    const uint64_t layout = MN ? 1ull : 2ull;
+    const uint32_t sbo = MN ? 512u : (BK == 32 ? 1024u : 512u);
+    const uint64_t layout = MN ? 1ull : (BK == 32 ? 2ull : 4ull);
     return static_cast<uint64_t>((addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>((lbo >> 4) & 0x3fffu) << 16) |
            (static_cast<uint64_t>((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46) | (layout << 61);
 }
@@ -137,12 +138,15 @@ struct GemmArgs {
 
 // A_MN / B_MN: operand is MN-major (stored row-major as [K, MN]); B_PRE: B arrives pre-split
 // (two tensor maps: hi, lo) so only A is split in shared memory.
-template <int BN, bool A_MN, bool B_MN, bool B_PRE>
+template <int BN, int BK, bool A_MN, bool B_MN, bool B_PRE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_hi,
                    const __grid_constant__ CUtensorMap tmap_b_lo, GemmArgs args) {
-    constexpr uint32_t kABytes = kBM * 128;                     // 16 KB: 128 rows x 32 fp32 (either major)
-    constexpr uint32_t kBBytes = BN * 128;
+    constexpr int kStages = BK == 32 ? 2 : 4;
+    constexpr int kBK = BK;
+    constexpr uint32_t kSlab = BK * 128;                        // one MN-major slab: BK k-rows x 32 MN elements
+    constexpr uint32_t kABytes = kBM * BK * 4;                  // 128 rows x BK fp32 (either major)
+    constexpr uint32_t kBBytes = BN * BK * 4;
     constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
     constexpr uint32_t kTxBytes = kABytes + (B_PRE ? 2 : 1) * kBBytes;
     constexpr uint32_t kTmemCols = kAccStages * BN;             // 512 for BN = 256
@@ -205,15 +209,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     bar_expect_tx(bar_full(stage), kTxBytes);
                     if (A_MN) {
 #pragma unroll
-                        for (int s = 0; s < kBM / 32; ++s) tma_load_2d(sa + s * 4096u, &tmap_a, m0 + 32 * s, kb * kBK, bar_full(stage));
+                        for (int s = 0; s < kBM / 32; ++s) tma_load_2d(sa + s * kSlab, &tmap_a, m0 + 32 * s, kb * kBK, bar_full(stage));
                     } else {
                         tma_load_2d(sa, &tmap_a, kb * kBK, m0, bar_full(stage));
                     }
                     if (B_MN) {
 #pragma unroll
                         for (int s = 0; s < BN / 32; ++s) {
-                            tma_load_2d(sb_hi + s * 4096u, &tmap_b_hi, n0 + 32 * s, kb * kBK, bar_full(stage));
-                            if (B_PRE) tma_load_2d(sb_lo + s * 4096u, &tmap_b_lo, n0 + 32 * s, kb * kBK, bar_full(stage));
+                            tma_load_2d(sb_hi + s * kSlab, &tmap_b_hi, n0 + 32 * s, kb * kBK, bar_full(stage));
+                            if (B_PRE) tma_load_2d(sb_lo + s * kSlab, &tmap_b_lo, n0 + 32 * s, kb * kBK, bar_full(stage));
                         }
                     } else {
                         tma_load_2d(sb_hi, &tmap_b_hi, kb * kBK, n0, bar_full(stage));
@@ -250,10 +254,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         // MN-major: the next group of 8 k-rows = 1024 B further.
                         const uint32_t ao = A_MN ? j * 1024u : j * 32u;
                         const uint32_t bo = B_MN ? j * 1024u : j * 32u;
-                        const uint64_t a_hi = smem_desc<A_MN>(sa_hi + ao, 4096);
-                        const uint64_t a_lo = smem_desc<A_MN>(sa_lo + ao, 4096);
-                        const uint64_t b_hi = smem_desc<B_MN>(sb_hi + bo, 4096);
-                        const uint64_t b_lo = smem_desc<B_MN>(sb_lo + bo, 4096);
+                        const uint64_t a_hi = smem_desc<A_MN, BK>(sa_hi + ao, kSlab);
+                        const uint64_t a_lo = smem_desc<A_MN, BK>(sa_lo + ao, kSlab);
+                        const uint64_t b_hi = smem_desc<B_MN, BK>(sb_hi + bo, kSlab);
+                        const uint64_t b_lo = smem_desc<B_MN, BK>(sb_lo + bo, kSlab);
                         umma_tf32(d, a_lo, b_hi, kIdesc, accumulate);     // small terms first
                         umma_tf32(d, a_hi, b_lo, kIdesc, 1u);
                         umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
@@ -363,11 +367,15 @@ static EncodeTiledFn encode_fn() {
     }
     return fn;
 }
-// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols], zero fill.  box_rows == 32 is
-// the MN-major operand form (32 k-rows x 32 MN elements per box): 128B swizzle with a 32-byte atom;
-// otherwise the K-major form: plain 128B swizzle.
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-    const CUtensorMapSwizzle swz = box_rows == 32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+// 2-D fp32 row-major [rows, cols] tensor, zero fill.
+//   K-major operand  (mn = false): box = [box_rows, bk cols], 128B (bk = 32) or 64B (bk = 16) swizzle;
+//   MN-major operand (mn = true) : box = [bk k-rows, 32 MN cols], 128B swizzle with a 32-byte atom.
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, bool mn, int bk,
+                    int box_rows) {
+    const CUtensorMapSwizzle swz = mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                      : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    const int box_cols = mn ? 32 : bk;
+    if (mn) box_rows = bk;
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -375,7 +383,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     }
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -388,11 +396,11 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     return B200MP_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool B_PRE>
+template <int BN, int BK, bool A_MN, bool B_MN, bool B_PRE>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const GemmArgs& args,
                        cudaStream_t stream) {
-    constexpr size_t smem = kStages * (2 * kBM * 128 + 2 * BN * 128) + 256 + 1024;
-    auto kfn = gemm_tf32x3_kernel<BN, A_MN, B_MN, B_PRE>;
+    constexpr size_t smem = (BK == 32 ? 2 : 4) * (2 * kBM * BK * 4 + 2 * BN * BK * 4) + 256 + 1024;
+    auto kfn = gemm_tf32x3_kernel<BN, BK, A_MN, B_MN, B_PRE>;
     B200MP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int n_work = args.n_tiles_m * args.n_tiles_n * args.n_splits;
     const int grid = n_work < num_sms() ? n_work : num_sms();
@@ -407,84 +415,50 @@ static bool ok16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 using namespace b200mp;
 
-extern "C" int b200mp_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream) {
-    B200MP_CHECK_ARG(n >= 0);
-    if (n == 0) return B200MP_OK;
-    B200MP_CHECK_ARG(w && w_hi && w_lo);
-    split_tf32_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, w_hi, w_lo, n);
-    B200MP_LAUNCH_CHECK();
-    return B200MP_OK;
-}
+namespace b200mp {
+int get_option_gemm_bk();   // 16 or 32 (b200mp_set_option("gemm_bk", ...)); default = measured best
 
-// y[M,N] = x[M,K] . w[N,K]^T  with w pre-split.  N in {64,128,256} (or a multiple of 256), K % 32 == 0.
-extern "C" int b200mp_linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, float* y, int64_t m, int64_t n,
-                                    int64_t k, void* stream) {
-    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
-    if (m == 0) return B200MP_OK;
-    B200MP_CHECK_ARG(x && w_hi && w_lo && y && ok16(x) && ok16(w_hi) && ok16(w_lo) && ok16(y));
-    if (k % 32 != 0 || !(n == 64 || n == 128 || n % 256 == 0) || m > 0x7fffffffLL) {
-        set_error("linear_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
-        return B200MP_ERR_UNSUPPORTED;
-    }
+static bool width_ok(int64_t w) { return w == 64 || w == 128 || (w > 0 && w % 256 == 0); }
+
+// y[M,N] = x[M,K] . w[N,K]^T
+template <int BK>
+static int run_forward(const float* x, const float* w_hi, const float* w_lo, float* y, int64_t m, int64_t n, int64_t k,
+                       cudaStream_t s) {
     const int bn = n >= 256 ? 256 : static_cast<int>(n);
     CUtensorMap ta, tbh, tbl;
     int rc;
-    if ((rc = make_map(&ta, x, m, k, k, kBM))) return rc;
-    if ((rc = make_map(&tbh, w_hi, n, k, k, bn))) return rc;
-    if ((rc = make_map(&tbl, w_lo, n, k, k, bn))) return rc;
-    GemmArgs a{y, m, n, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n / bn), static_cast<int>(k / 32), static_cast<int>(k / 32), 1};
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (bn == 256) return launch_gemm<256, false, false, true>(ta, tbh, tbl, a, s);
-    if (bn == 128) return launch_gemm<128, false, false, true>(ta, tbh, tbl, a, s);
-    return launch_gemm<64, false, false, true>(ta, tbh, tbl, a, s);
+    if ((rc = make_map(&ta, x, m, k, k, false, BK, kBM))) return rc;
+    if ((rc = make_map(&tbh, w_hi, n, k, k, false, BK, bn))) return rc;
+    if ((rc = make_map(&tbl, w_lo, n, k, k, false, BK, bn))) return rc;
+    const int kb = static_cast<int>(k / BK);
+    GemmArgs a{y, m, n, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n / bn), kb, kb, 1};
+    if (bn == 256) return launch_gemm<256, BK, false, false, true>(ta, tbh, tbl, a, s);
+    if (bn == 128) return launch_gemm<128, BK, false, false, true>(ta, tbh, tbl, a, s);
+    return launch_gemm<64, BK, false, false, true>(ta, tbh, tbl, a, s);
 }
-
-// gx[M,K] = g[M,N] . w[N,K]  (w pre-split, read MN-major exactly as stored).  K in {64,128,256,..}, N % 32 == 0.
-extern "C" int b200mp_linear_grad_input_tf32x3(const float* g, const float* w_hi, const float* w_lo, float* gx, int64_t m,
-                                               int64_t n, int64_t k, void* stream) {
-    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
-    if (m == 0) return B200MP_OK;
-    B200MP_CHECK_ARG(g && w_hi && w_lo && gx && ok16(g) && ok16(w_hi) && ok16(w_lo) && ok16(gx));
-    if (n % 32 != 0 || !(k == 64 || k == 128 || k % 256 == 0) || m > 0x7fffffffLL) {
-        set_error("linear_grad_input_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
-        return B200MP_ERR_UNSUPPORTED;
-    }
-    const int bn = k >= 256 ? 256 : static_cast<int>(k);          // output width is k
+// gx[M,K] = g[M,N] . w[N,K]   (B = w read MN-major exactly as stored: [K' = n rows][N' = k cols])
+template <int BK>
+static int run_grad_input(const float* g, const float* w_hi, const float* w_lo, float* gx, int64_t m, int64_t n, int64_t k,
+                          cudaStream_t s) {
+    const int bn = k >= 256 ? 256 : static_cast<int>(k);
     CUtensorMap ta, tbh, tbl;
     int rc;
-    if ((rc = make_map(&ta, g, m, n, n, kBM))) return rc;          // A = g: K-major, reduction dim = n
-    if ((rc = make_map(&tbh, w_hi, n, k, k, 32))) return rc;       // B stored [K' = n rows][N' = k cols]: MN-major, 32x32 boxes
-    if ((rc = make_map(&tbl, w_lo, n, k, k, 32))) return rc;
-    GemmArgs a{gx, m, k, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(k / bn), static_cast<int>(n / 32), static_cast<int>(n / 32), 1};
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (bn == 256) return launch_gemm<256, false, true, true>(ta, tbh, tbl, a, s);
-    if (bn == 128) return launch_gemm<128, false, true, true>(ta, tbh, tbl, a, s);
-    return launch_gemm<64, false, true, true>(ta, tbh, tbl, a, s);
+    if ((rc = make_map(&ta, g, m, n, n, false, BK, kBM))) return rc;
+    if ((rc = make_map(&tbh, w_hi, n, k, k, true, BK, 0))) return rc;
+    if ((rc = make_map(&tbl, w_lo, n, k, k, true, BK, 0))) return rc;
+    const int kb = static_cast<int>(n / BK);
+    GemmArgs a{gx, m, k, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(k / bn), kb, kb, 1};
+    if (bn == 256) return launch_gemm<256, BK, false, true, true>(ta, tbh, tbl, a, s);
+    if (bn == 128) return launch_gemm<128, BK, false, true, true>(ta, tbh, tbl, a, s);
+    return launch_gemm<64, BK, false, true, true>(ta, tbh, tbl, a, s);
 }
-
-extern "C" int64_t b200mp_linear_grad_weight_workspace_bytes(int64_t m, int64_t n, int64_t k) {
-    if (m < 0 || n <= 0 || k <= 0) return B200MP_ERR_INVALID_ARG;
-    return static_cast<int64_t>(num_sms()) * n * k * 4 + 256;
-}
-
-// gw[N,K] = g[M,N]^T . x[M,K]: both operands MN-major as stored, deterministic split-K over the M rows.
-// N % 128 == 0, K in {64,128,256,...}.  workspace from b200mp_linear_grad_weight_workspace_bytes().
-extern "C" int b200mp_linear_grad_weight_tf32x3(const float* g, const float* x, float* gw, int64_t m, int64_t n, int64_t k,
-                                                void* workspace, int64_t workspace_bytes, void* stream) {
-    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (m == 0) {
-        B200MP_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * n * k, s));
-        return B200MP_OK;
-    }
-    B200MP_CHECK_ARG(g && x && gw && workspace && ok16(g) && ok16(x) && ok16(gw) && ok16(workspace));
-    if (n % 128 != 0 || !(k == 64 || k == 128 || k % 256 == 0)) {
-        set_error("linear_grad_weight_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
-        return B200MP_ERR_UNSUPPORTED;
-    }
+// gw[N,K] = g[M,N]^T . x[M,K]: both operands MN-major as stored, split-K over the M rows
+template <int BK>
+static int run_grad_weight(const float* g, const float* x, float* gw, int64_t m, int64_t n, int64_t k, void* workspace,
+                           int64_t workspace_bytes, cudaStream_t s) {
     const int bn = k >= 256 ? 256 : static_cast<int>(k);
     const int tiles = static_cast<int>((n / kBM) * (k / bn));
-    const int64_t kblocks = ceil_div(m, 32);
+    const int64_t kblocks = ceil_div(m, BK);
     if (kblocks > 0x7fffffffLL) return B200MP_ERR_UNSUPPORTED;
     int splits = num_sms() / tiles;
     if (splits < 1) splits = 1;
@@ -497,15 +471,76 @@ extern "C" int b200mp_linear_grad_weight_tf32x3(const float* g, const float* x, 
     }
     CUtensorMap ta, tb;
     int rc;
-    if ((rc = make_map(&ta, g, m, n, n, 32))) return rc;           // A[m'=n-index, k'=row]: stored [K' rows][M' cols]
-    if ((rc = make_map(&tb, x, m, k, k, 32))) return rc;
-    GemmArgs a{static_cast<float*>(workspace), n, k, static_cast<int>(n / kBM), static_cast<int>(k / bn), static_cast<int>(kblocks), kbps, splits};
-    if (bn == 256) rc = launch_gemm<256, true, true, false>(ta, tb, tb, a, s);
-    else if (bn == 128) rc = launch_gemm<128, true, true, false>(ta, tb, tb, a, s);
-    else rc = launch_gemm<64, true, true, false>(ta, tb, tb, a, s);
+    if ((rc = make_map(&ta, g, m, n, n, true, BK, 0))) return rc;   // A[m' = n-index, k' = row]: stored [K' rows][M' cols]
+    if ((rc = make_map(&tb, x, m, k, k, true, BK, 0))) return rc;
+    GemmArgs a{static_cast<float*>(workspace), n, k, static_cast<int>(n / kBM), static_cast<int>(k / bn),
+               static_cast<int>(kblocks), kbps, splits};
+    if (bn == 256) rc = launch_gemm<256, BK, true, true, false>(ta, tb, tb, a, s);
+    else if (bn == 128) rc = launch_gemm<128, BK, true, true, false>(ta, tb, tb, a, s);
+    else rc = launch_gemm<64, BK, true, true, false>(ta, tb, tb, a, s);
     if (rc) return rc;
     const int64_t total = n * k;
-    splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, s>>>(static_cast<const float*>(workspace), gw, total, splits);
+    splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, s>>>(static_cast<const float*>(workspace), gw,
+                                                                                      total, splits);
     B200MP_LAUNCH_CHECK();
     return B200MP_OK;
+}
+}  // namespace b200mp
+
+extern "C" int b200mp_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream) {
+    B200MP_CHECK_ARG(n >= 0);
+    if (n == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(w && w_hi && w_lo);
+    split_tf32_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, w_hi, w_lo, n);
+    B200MP_LAUNCH_CHECK();
+    return B200MP_OK;
+}
+
+extern "C" int b200mp_linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, float* y, int64_t m, int64_t n,
+                                    int64_t k, void* stream) {
+    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
+    if (m == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(x && w_hi && w_lo && y && ok16(x) && ok16(w_hi) && ok16(w_lo) && ok16(y));
+    if (k % 32 != 0 || !width_ok(n) || m > 0x7fffffffLL) {
+        set_error("linear_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return get_option_gemm_bk() == 32 ? run_forward<32>(x, w_hi, w_lo, y, m, n, k, s) : run_forward<16>(x, w_hi, w_lo, y, m, n, k, s);
+}
+
+extern "C" int b200mp_linear_grad_input_tf32x3(const float* g, const float* w_hi, const float* w_lo, float* gx, int64_t m,
+                                               int64_t n, int64_t k, void* stream) {
+    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
+    if (m == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(g && w_hi && w_lo && gx && ok16(g) && ok16(w_hi) && ok16(w_lo) && ok16(gx));
+    if (n % 32 != 0 || !width_ok(k) || m > 0x7fffffffLL) {
+        set_error("linear_grad_input_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return get_option_gemm_bk() == 32 ? run_grad_input<32>(g, w_hi, w_lo, gx, m, n, k, s)
+                                      : run_grad_input<16>(g, w_hi, w_lo, gx, m, n, k, s);
+}
+
+extern "C" int64_t b200mp_linear_grad_weight_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+    if (m < 0 || n <= 0 || k <= 0) return B200MP_ERR_INVALID_ARG;
+    return static_cast<int64_t>(num_sms()) * n * k * 4 + 256;
+}
+
+extern "C" int b200mp_linear_grad_weight_tf32x3(const float* g, const float* x, float* gw, int64_t m, int64_t n, int64_t k,
+                                                void* workspace, int64_t workspace_bytes, void* stream) {
+    B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (m == 0) {
+        B200MP_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * n * k, s));
+        return B200MP_OK;
+    }
+    B200MP_CHECK_ARG(g && x && gw && workspace && ok16(g) && ok16(x) && ok16(gw) && ok16(workspace));
+    if (n % 128 != 0 || !width_ok(k)) {
+        set_error("linear_grad_weight_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    return get_option_gemm_bk() == 32 ? run_grad_weight<32>(g, x, gw, m, n, k, workspace, workspace_bytes, s)
+                                      : run_grad_weight<16>(g, x, gw, m, n, k, workspace, workspace_bytes, s);
 }

@@ -3,18 +3,21 @@
 One process per GPU.  Rank r owns the contiguous node range [r*n, (r+1)*n): its feature rows, its
 output rows, and the CSR slice of its DESTINATIONS (the reference's closest notion is
 `EdgeIndex.sparse_narrow`, edge_index.py:1028-1133, which nothing in the reference calls).  Sources
-outside the range are *halo* rows.  Per aggregation pass there is exactly ONE exchange:
+outside the range are *halo* rows.  Per aggregation pass there is exactly ONE exchange, and it is
+hidden behind the local part of the sweep:
 
-    forward :  pack the rows my peers need (gather) -> all_to_all_single (NCCL over NVLink)
-               -> one gather-reduce over [local rows | halo rows] (two-segment source, no concat)
-    backward:  transposed gather-reduce -> the halo part of the result goes back with the mirror
-               all_to_all_single and is added into the owners' rows (index_add).
+    forward :  pack the rows my peers need (gather) -> all_to_all_single (NCCL over NVLink, async)
+               || gather-reduce over the LOCAL-source edges (~p_local of the work)
+               -> gather-reduce over the HALO-source edges, accumulated into the same rows
+    backward:  transposed gather-reduce of the HALO sources first (small) -> mirror all_to_all (async)
+               || transposed gather-reduce of the LOCAL sources
+               -> returned rows added into their owners' rows (red.global.add.v4)
 
 Everything else (degrees, gcn_norm, softmax, max, mean) is per destination, hence local.  The plan
 (unique remote ids grouped by owner, send lists, relabelled columns) is integer set-up work done
 once per graph with device-agnostic torch ops, so the same code is exercised on CPU with the gloo
 backend by tests/test_dist_gloo.py.  The reference has no counterpart of this module; correctness
-is shard-vs-unsharded equality against the single-process oracle.
+is shard-vs-unsharded equality against the single-process engine and oracle.
 """
 from __future__ import annotations
 
@@ -46,11 +49,18 @@ class HaloPlan:
         return int(self.send_index.numel())
 
 
-def _all_to_all_rows(out: Tensor, inp: Tensor, out_counts: List[int], in_counts: List[int], group) -> Tensor:
+class _Done:
+    def wait(self):
+        return None
+
+
+def _all_to_all_rows(out: Tensor, inp: Tensor, out_counts: List[int], in_counts: List[int], group, async_op=False):
+    """Variable-size row exchange; returns a handle with .wait() (a no-op handle for world == 1)."""
     if dist.get_world_size(group) == 1:
-        return out
-    dist.all_to_all_single(out, inp, output_split_sizes=out_counts, input_split_sizes=in_counts, group=group)
-    return out
+        return _Done()
+    work = dist.all_to_all_single(out, inp, output_split_sizes=out_counts, input_split_sizes=in_counts, group=group,
+                                  async_op=async_op)
+    return work if async_op else _Done()
 
 
 def build_halo_plan(src_global: Tensor, lo: int, n_local: int, group=None):
@@ -75,7 +85,6 @@ def build_halo_plan(src_global: Tensor, lo: int, n_local: int, group=None):
     send_index = want - lo                                     # local row ids, grouped by requester
     if want.numel():
         assert int(send_index.min()) >= 0 and int(send_index.max()) < n_local, "halo request outside the owner's range"
-    # relabel
     slot = torch.searchsorted(halo_ids, src_global.clamp(min=0)) if halo_ids.numel() else torch.zeros_like(src_global)
     src_rel = torch.where(is_remote, slot + n_local, src_global - lo)
     plan = HaloPlan(rank, world, lo, n_local, halo_ids, recv_counts, send_index, send_counts)
@@ -89,20 +98,32 @@ def _pack(x_local: Tensor, index: Tensor) -> Tensor:
     return x_local.index_select(0, index)
 
 
-def exchange_halo(plan: HaloPlan, x_local: Tensor, group=None) -> Tensor:
-    """Forward exchange: returns the halo rows [n_halo, F] in halo_ids order."""
+def exchange_halo_start(plan: HaloPlan, x_local: Tensor, group=None):
+    """Starts the forward exchange; returns (halo_rows_buffer, handle).  handle.wait() makes the
+    current stream wait for the rows to have arrived."""
     group = group if group is not None else dist.group.WORLD
     send = _pack(x_local, plan.send_index)
     recv = torch.empty((plan.n_halo, ) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
-    return _all_to_all_rows(recv, send, plan.recv_counts, plan.send_counts, group)
+    work = _all_to_all_rows(recv, send, plan.recv_counts, plan.send_counts, group, async_op=x_local.is_cuda)
+    return recv, work, send   # `send` is returned so it stays alive until the exchange completes
 
 
-def return_halo(plan: HaloPlan, g_halo: Tensor, g_local: Tensor, group=None) -> Tensor:
-    """Backward exchange: sends per-halo-row contributions back to their owners and adds them into
-    g_local in place (rows listed in send_index)."""
+def exchange_halo(plan: HaloPlan, x_local: Tensor, group=None) -> Tensor:
+    """Blocking forward exchange: the halo rows [n_halo, F] in halo_ids order."""
+    recv, work, _ = exchange_halo_start(plan, x_local, group)
+    work.wait()
+    return recv
+
+
+def return_halo_start(plan: HaloPlan, g_halo: Tensor, group=None):
     group = group if group is not None else dist.group.WORLD
+    g_halo = g_halo.contiguous()
     recv = torch.empty((plan.n_send, ) + tuple(g_halo.shape[1:]), dtype=g_halo.dtype, device=g_halo.device)
-    _all_to_all_rows(recv, g_halo.contiguous(), plan.send_counts, plan.recv_counts, group)
+    work = _all_to_all_rows(recv, g_halo, plan.send_counts, plan.recv_counts, group, async_op=g_halo.is_cuda)
+    return recv, work, g_halo
+
+
+def return_halo_finish(plan: HaloPlan, recv: Tensor, g_local: Tensor) -> Tensor:
     if plan.n_send:
         if g_local.is_cuda and g_local.dtype == torch.float32 and g_local.dim() == 2:
             from . import ops
@@ -110,6 +131,14 @@ def return_halo(plan: HaloPlan, g_halo: Tensor, g_local: Tensor, group=None) -> 
         else:
             g_local.index_add_(0, plan.send_index, recv)
     return g_local
+
+
+def return_halo(plan: HaloPlan, g_halo: Tensor, g_local: Tensor, group=None) -> Tensor:
+    """Blocking backward exchange: per-halo-row contributions go back to their owners and are added
+    into g_local in place (rows listed in send_index)."""
+    recv, work, _ = return_halo_start(plan, g_halo, group)
+    work.wait()
+    return return_halo_finish(plan, recv, g_local)
 
 
 def shard_self_loops(src_global: Tensor, dst_global: Tensor, lo: int, n_local: int):
@@ -121,12 +150,17 @@ def shard_self_loops(src_global: Tensor, dst_global: Tensor, lo: int, n_local: i
 
 
 class ShardedGCNGraph:
-    """One rank's slice of a gcn_norm'ed graph: CSR over the owned destinations, columns relabelled
-    to [local | halo], D^-1/2 (A+I) D^-1/2 weights computed with the degrees of remote sources
-    fetched by one halo exchange at build time."""
+    """One rank's slice of a gcn_norm'ed graph, split by source locality:
+      g_local : CSR over the owned destinations with the LOCAL-source edges (+ its transpose)
+      g_halo  : CSR over the owned destinations with the HALO-source edges (+ its transpose, whose
+                rows are the halo slots)
+    D^-1/2 (A+I) D^-1/2 weights use the degrees of remote sources fetched by one halo exchange at
+    build time.  `graph` is kept as an alias of g_local for reporting."""
 
-    def __init__(self, graph, plan: HaloPlan, group):
-        self.graph, self.plan, self.group = graph, plan, group
+    def __init__(self, g_local, g_halo, plan: HaloPlan, group):
+        self.g_local, self.g_halo, self.plan, self.group = g_local, g_halo, plan, group
+        self.graph = g_local
+        self.num_edges = g_local.num_edges + (g_halo.num_edges if g_halo is not None else 0)
 
     @classmethod
     def build(cls, edge_index_global: Tensor, lo: int, n_local: int, n_total: int, group=None,
@@ -138,48 +172,61 @@ class ShardedGCNGraph:
         if add_self_loops:
             src, dst = shard_self_loops(src, dst, lo, n_local)
         plan, src_rel = build_halo_plan(src, lo, n_local, group)
-        g = CSRGraph(src_rel, dst - lo, n_local + plan.n_halo, n_local)
+        dst_l = dst - lo
         # degrees are sums over incoming edges => local; remote sources' dinv comes by halo exchange
-        deg = g.in_degree().to(torch.float32)
+        deg = ops.degree(dst_l, n_local).to(torch.float32)
         if improved and add_self_loops:
             deg = deg + 1.0                                    # loop weight 2 instead of 1
         dinv = deg.pow(-0.5)
         dinv.masked_fill_(dinv == float("inf"), 0.0)
         dinv_halo = exchange_halo(plan, dinv.view(-1, 1), group).view(-1)
         dinv_cat = torch.cat([dinv, dinv_halo])
-        w = ops.gather_rows(dinv_cat.view(-1, 1), g.col).view(-1) * ops.gather_rows(dinv.view(-1, 1), g.dst_csr).view(-1)
+        w = ops.gather_rows(dinv_cat.view(-1, 1), src_rel).view(-1) * ops.gather_rows(dinv.view(-1, 1), dst_l).view(-1)
         if improved and add_self_loops:
-            is_loop = g.col.long() == g.dst_csr.long()
-            w = torch.where(is_loop, w * 2.0, w)
-        g.val = w
-        g.build_transpose()
-        return cls(g, plan, group)
+            w = torch.where(src_rel == dst_l, w * 2.0, w)
+        is_halo = src_rel >= n_local
+        keep = ~is_halo
+        g_local = CSRGraph(src_rel[keep], dst_l[keep], n_local, n_local, w[keep])
+        g_local.build_transpose()
+        g_halo = None
+        if plan.n_halo:
+            g_halo = CSRGraph(src_rel[is_halo] - n_local, dst_l[is_halo], plan.n_halo, n_local, w[is_halo])
+            g_halo.build_transpose()
+        return cls(g_local, g_halo, plan, group)
 
 
 class _ShardedAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local: Tensor, bias: Optional[Tensor], shard: ShardedGCNGraph):
         from . import ops
-        g, plan = shard.graph, shard.plan
+        gl, gh, plan = shard.g_local, shard.g_halo, shard.plan
         x_local = x_local.contiguous()
-        halo = exchange_halo(plan, x_local, shard.group)
         ctx.shard = shard
         ctx.has_bias = bias is not None
-        return ops.spmm_csr(g.rowptr, g.col, g.val, x_local, g.num_dst, "sum", g.plan, bias=bias,
-                            x_halo=halo if plan.n_halo else None)
+        if gh is None:
+            return ops.spmm_csr(gl.rowptr, gl.col, gl.val, x_local, gl.num_dst, "sum", gl.plan, bias=bias)
+        halo, work, _keep = exchange_halo_start(plan, x_local, shard.group)          # async over NVLink
+        out = ops.spmm_csr(gl.rowptr, gl.col, gl.val, x_local, gl.num_dst, "sum", gl.plan, bias=bias)   # overlaps
+        work.wait()
+        ops.spmm_csr(gh.rowptr, gh.col, gh.val, halo, gh.num_dst, "sum", gh.plan, out=out, accumulate=True)
+        return out
 
     @staticmethod
     def backward(ctx, grad_out: Tensor):
         from . import ops
         shard = ctx.shard
-        g, plan = shard.graph, shard.plan
+        gl, gh, plan = shard.g_local, shard.g_halo, shard.plan
         grad_out = grad_out.contiguous()
         gx = gb = None
         if ctx.needs_input_grad[0]:
-            g_cat = ops.spmm_csr(g.rowptr_t, g.col_t, g.val_t, grad_out, g.num_src, "sum", g.plan_t)
-            g_local = g_cat[:plan.n_local]
-            return_halo(plan, g_cat[plan.n_local:], g_local, shard.group)
-            gx = g_local
+            if gh is None:
+                gx = ops.spmm_csr(gl.rowptr_t, gl.col_t, gl.val_t, grad_out, gl.num_src, "sum", gl.plan_t)
+            else:
+                g_halo = ops.spmm_csr(gh.rowptr_t, gh.col_t, gh.val_t, grad_out, gh.num_src, "sum", gh.plan_t)
+                recv, work, _keep = return_halo_start(plan, g_halo, shard.group)     # async over NVLink
+                gx = ops.spmm_csr(gl.rowptr_t, gl.col_t, gl.val_t, grad_out, gl.num_src, "sum", gl.plan_t)  # overlaps
+                work.wait()
+                return_halo_finish(plan, recv, gx)
         if ctx.has_bias and ctx.needs_input_grad[1]:
             gb = grad_out.sum(0, dtype=torch.float32)
         return gx, gb, None
@@ -190,7 +237,7 @@ def sharded_aggregate(x_local: Tensor, shard: ShardedGCNGraph, bias: Optional[Te
 
 
 def sharded_gcn_conv(conv, x_local: Tensor, shard: ShardedGCNGraph) -> Tensor:
-    """GCNConv.forward on one shard: local dense transform, halo exchange of the transformed rows,
-    fused aggregate (+ bias).  Weight gradients are per-rank partial sums (all-reduce them like
-    DDP does; bench.py includes that all_reduce in the timed step)."""
+    """GCNConv.forward on one shard: local dense transform, halo exchange of the transformed rows
+    hidden behind the local-edge sweep, fused aggregate (+ bias).  Weight gradients are per-rank
+    partial sums (all-reduce them like DDP does; bench.py includes that all_reduce in the step)."""
     return sharded_aggregate(conv.lin(x_local), shard, conv.bias)

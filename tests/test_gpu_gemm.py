@@ -20,9 +20,17 @@ def _check(got, ref64, scale64, tol=1e-5):
     assert (err <= bound).all(), f"max err/scale {float((err / (scale64 + 1e-30)).max()):.3e}"
 
 
+@pytest.fixture(params=[32, 16], ids=["bk32", "bk16"])
+def gemm_bk(request):
+    from pytorch_geometric_b200 import ops
+    ops.set_option("gemm_bk", request.param)      # k-block width: 2 x 96 KB or 4 x 48 KB pipeline stages
+    yield request.param
+    ops.set_option("gemm_bk", 32)
+
+
 @pytest.mark.parametrize("m", [1, 127, 128, 129, 1000, 20011])
 @pytest.mark.parametrize("n,k", [(256, 256), (128, 256), (256, 128), (128, 64), (512, 256)])
-def test_linear_tf32x3_forward_and_grads(m, n, k):
+def test_linear_tf32x3_forward_and_grads(m, n, k, gemm_bk):
     g = torch.Generator(device=DEV).manual_seed(m * 7 + n + k)
     x = torch.randn(m, k, device=DEV, generator=g)
     w = torch.randn(n, k, device=DEV, generator=g) / k ** 0.5
