@@ -233,17 +233,32 @@ def run_b200(args):
         E_prime = graph.num_edges
         fwd = lambda xx: conv(xx, graph)                                     # noqa: E731
     else:
-        from pytorch_geometric_b200 import dist as pdist
         ei = synth_graph(N, E, 1 + rank, dev, lo=rank * N, total_nodes=world * N, p_local=args.p_local)
-        shard = pdist.ShardedGCNGraph.build(ei, rank * N, N, world * N, dist.group.WORLD)
+        shard = None
+        if args.dist == "p2p":
+            # halo exchange fused into the gather kernel over NVLink peer memory (dist_p2p.py)
+            try:
+                from pytorch_geometric_b200 import dist_p2p
+                shard = dist_p2p.PeerShardedGCNGraph.build(ei, rank * N, N, world * N, F, dist.group.WORLD)
+                fwd = lambda xx: dist_p2p.peer_sharded_gcn_conv(conv, xx, shard)    # noqa: E731
+            except Exception as exc:                                  # symmetric memory unavailable on this box
+                print(f"[bench] symmetric-memory path unavailable ({exc!r}); using the NCCL all_to_all path", file=sys.stderr)
+                args.dist = "nccl"
+                shard = None
+        if shard is None:
+            from pytorch_geometric_b200 import dist as pdist
+            shard = pdist.ShardedGCNGraph.build(ei, rank * N, N, world * N, dist.group.WORLD)
+            fwd = lambda xx: pdist.sharded_gcn_conv(conv, xx, shard)             # noqa: E731
         del ei
         E_prime = shard.num_edges
-        fwd = lambda xx: pdist.sharded_gcn_conv(conv, xx, shard)             # noqa: E731
         graph = shard.graph
     torch.cuda.synchronize()
 
     x = torch.randn(N, F, device=dev).requires_grad_()
-    gout = torch.randn(N, F, device=dev)
+    if world > 1 and args.dist == "p2p":
+        gout = shard.gout.normal_()                                   # upstream gradient produced in the symmetric buffer
+    else:
+        gout = torch.randn(N, F, device=dev)
 
     def step():
         x.grad = None
@@ -380,7 +395,10 @@ def run_b200(args):
                                    f" (E'={E_prime} with self loops), fp32, int32 CSR, graph cached (cached=True)",
                        "nodes_per_gpu": N, "edges_per_gpu": E, "feat": F, "layers": 1,
                        "l2_policy": "inputs (x, grad, CSR > 10 GB) are far larger than the 126 MB L2; no explicit flush",
-                       "parallelism": "single GPU" if world == 1 else f"node-range sharding x{world}, p_local={args.p_local}, halo all_to_all",
+                       "parallelism": "single GPU" if world == 1 else (
+                           f"node-range sharding x{world}, p_local={args.p_local}, " +
+                           ("halo rows gathered over NVLink peer memory inside the kernel (symmetric memory)"
+                            if args.dist == "p2p" else "halo all_to_all (NCCL) overlapped with the local sweep")),
                        "gemm": ("hand-written tcgen05 3xTF32 (fp32-accurate, csrc/gemm_tf32x3.cu)" if args.dense == "tf32x3"
                                 else "torch.nn.functional.linear (cuBLAS fp32, allow_tf32=False)"),
                        "long_rows": graph.plan.n_long, "chunks": graph.plan.n_chunks,
@@ -416,6 +434,8 @@ def main():
     ap.add_argument("--nodes", type=int, default=10_000_000, help="nodes per GPU")
     ap.add_argument("--edges", type=int, default=100_000_000, help="edges per GPU")
     ap.add_argument("--feat", type=int, default=256)
+    ap.add_argument("--dist", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: halo rows gathered over NVLink peer memory inside the kernel, or NCCL all_to_all")
     ap.add_argument("--p-local", type=float, default=0.95, help="fraction of sources inside the owner's range (N>1)")
     ap.add_argument("--cpu-nodes", type=int, default=250_000)
     ap.add_argument("--cpu-edges", type=int, default=2_500_000)

@@ -139,13 +139,18 @@ int b200mp_csr_plan_fill(const void* rowptr, int64_t n_rows, int64_t chunk, int6
  * are read from x_halo[c - n_local_cols, :] (the rows received by the halo all_to_all) so local
  * and remote rows are never concatenated (n_cols = n_local_cols + #halo rows).
  * flags bit 0 (accumulate, sum only, no bias): out[i,:] += result for rows that have edges and
- * rows without edges are left untouched -- adds the halo-edge part after the local-edge sweep. */
+ * rows without edges are left untouched -- adds the halo-edge part after the local-edge sweep.
+ * peer_ptrs (nullable, DEVICE array of uint64 addresses, one per GPU) + peer_rows: the source
+ * matrix is sharded by contiguous row ranges of peer_rows rows over the GPUs of the box and
+ * peer_ptrs[r] is rank r's peer-mapped base address (torch symmetric memory / CUDA IPC); column c
+ * is then gathered from peer_ptrs[c / peer_rows] + (c % peer_rows) * row_bytes, i.e. remote rows
+ * come straight over NVLink inside this kernel -- the collective is fused into the gather. */
 int b200mp_spmm_csr(const void* rowptr, const void* col, const float* val, const void* x,
                     void* out, int64_t n_rows, int64_t n_cols, int64_t feat, int reduce,
                     const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
                     int64_t n_chunks, int64_t chunk, float* partials, const float* bias,
-                    const void* x_halo, int64_t n_local_cols, int flags, int idx_dtype,
-                    int val_dtype, void* stream);
+                    const void* x_halo, int64_t n_local_cols, int flags, const void* peer_ptrs,
+                    int64_t peer_rows, int idx_dtype, int val_dtype, void* stream);
 
 /* Segmented reduce without gather: out[i,:] = REDUCE_{e in [ptr[i], ptr[i+1])} src[e,:].
  * Replaces utils/_segment.py:11-50 (torch._segment_reduce / torch_scatter.segment_csr) and the

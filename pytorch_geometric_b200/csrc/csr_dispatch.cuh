@@ -24,7 +24,7 @@ int csr_reduce_variant(const I* rowptr, const I* col, const float* val, const T*
     // issue-bound at 6 warps/SM) -- so "auto" is the lane-group kernel; the TMA variant stays
     // selectable for the A/B evidence and further tuning.
     const int impl = get_option_spmm_impl();
-    if (tma_ok && impl == 2 && !plan.accumulate)
+    if (tma_ok && impl == 2 && !plan.accumulate && !plan.peers)
         return csr_tma_launch<T, I, RED, GATHER>(rowptr, col, val, x, out, n_rows, feat, is_mean, inf_to_zero, plan,
                                                  bias, stream);
     return csr_reduce_dispatch<T, I, RED, GATHER>(rowptr, col, val, x, out, n_rows, feat, is_mean, inf_to_zero, plan,

@@ -38,7 +38,23 @@ struct LongRowPlan {
     // accumulate != 0: out[i,:] += result for rows that have edges (rows without edges are left
     // untouched) -- used to add the halo-edge contributions after the local-edge sweep (sum only)
     int accumulate;
+    // peers != nullptr: the source matrix is sharded over GPUs by contiguous row ranges of
+    // peer_rows rows; peers[r] is the (NVLink peer-mapped) base address of rank r's rows.  Column c
+    // is read from peers[c / peer_rows] + (c % peer_rows) * row_bytes -- remote rows are gathered
+    // straight over NVLink inside the kernel, no pack / exchange / unpack pass.
+    const unsigned long long* peers;
+    int64_t peer_rows;
 };
+
+// Base address of source row c for the three addressing modes (plain, [local | halo], peer table).
+__device__ __forceinline__ const char* row_base(const LongRowPlan& plan, const char* xb, const char* xb2, int64_t split,
+                                                size_t row_bytes, int64_t c) {
+    if (plan.peers) {
+        const int64_t r = c / plan.peer_rows;
+        return reinterpret_cast<const char*>(__ldg(plan.peers + r)) + static_cast<size_t>(c - r * plan.peer_rows) * row_bytes;
+    }
+    return (c < split ? xb : xb2) + static_cast<size_t>(c) * row_bytes;
+}
 
 // Decode a work item into (row, begin, end, is_chunk).  Items [0, n_chunks) are chunks of long
 // rows (scheduled first: they are the long poles), items [n_chunks, n_chunks + n_rows) are rows.
@@ -123,6 +139,8 @@ csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
                 if (lig < n) {
                     c_l = GATHER ? static_cast<int64_t>(ldg_idx(col + e0 + lig)) : (e0 + lig);
                     if (val) w_l = __ldg(val + e0 + lig);
+                    // each lane resolves the row address of ITS edge once; the address is what is broadcast
+                    c_l = static_cast<int64_t>(reinterpret_cast<uintptr_t>(row_base(plan, xb, xb2, split, row_bytes, c_l)));
                 }
                 for (int j = 0; j < n; j += UNR) {
                     Vec16 buf[UNR][VPL];
@@ -132,7 +150,7 @@ csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
                         const int64_t c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);
                         w[u] = __shfl_sync(0xffffffffu, w_l, (j + u) & 31);
                         if (j + u < n) {
-                            const char* p = (c < split ? xb : xb2) + static_cast<size_t>(c) * row_bytes + voff;
+                            const char* p = reinterpret_cast<const char*>(static_cast<uintptr_t>(c)) + voff;
 #pragma unroll
                             for (int k = 0; k < VPL; ++k)
                                 if (vvalid[k]) buf[u][k] = ldg_row16(p + static_cast<size_t>(k) * G * 16);
@@ -167,7 +185,7 @@ csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
                     if (e + u < end) {
                         const int64_t c = GATHER ? static_cast<int64_t>(ldg_idx(col + e + u)) : (e + u);
                         if (val) w[u] = __ldg(val + e + u);
-                        if (vvalid[0]) buf[u][0] = ldg_row16((c < split ? xb : xb2) + static_cast<size_t>(c) * row_bytes + voff);
+                        if (vvalid[0]) buf[u][0] = ldg_row16(row_base(plan, xb, xb2, split, row_bytes, c) + voff);
                     }
                 }
 #pragma unroll

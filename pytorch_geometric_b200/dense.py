@@ -51,10 +51,15 @@ def split_tf32(w: Tensor):
     return hi, lo
 
 
-def linear_forward(x: Tensor, w_hi: Tensor, w_lo: Tensor) -> Tensor:
+def linear_forward(x: Tensor, w_hi: Tensor, w_lo: Tensor, out: Tensor = None) -> Tensor:
     m, k = x.shape
     n = w_hi.size(0)
-    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    if out is None:
+        y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    else:
+        if out.shape != (m, n) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous fp32 [M, N] tensor")
+        y = out
     ops._timed("linear_tf32x3", 1, lib().b200mp_linear_tf32x3, x.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(),
                y.data_ptr(), m, n, k, ops._stream())
     return y

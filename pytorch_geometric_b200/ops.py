@@ -246,7 +246,8 @@ class LongRowPlan:
 # ------------------------------------------------------------------ the hot path
 def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_rows: int, reduce: str = "sum",
              plan: Optional[LongRowPlan] = None, out: Optional[Tensor] = None,
-             bias: Optional[Tensor] = None, x_halo: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+             bias: Optional[Tensor] = None, x_halo: Optional[Tensor] = None, accumulate: bool = False,
+             peer_ptrs: Optional[int] = None, peer_rows: int = 0) -> Tensor:
     """out[i,:] = REDUCE_{e in row i} val[e] * x[col[e],:] (+ bias)  (x: [n_cols, F] contiguous)."""
     _cuda(rowptr, col, val, x)
     if x.dim() != 2:
@@ -276,8 +277,8 @@ def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_ro
             raise ValueError("x_halo must be a contiguous [n_halo, F] tensor of x's dtype")
         n_local, n_cols = x.size(0), x.size(0) + x_halo.size(0)
     _timed("spmm_csr", 2 if args[2] else 1, lib().b200mp_spmm_csr, _p(rowptr), _p(col), _p(val), _p(x), _p(out),
-           n_rows, n_cols, F, REDUCE[reduce], *args, _p(bias), _p(x_halo), n_local, int(bool(accumulate)), it, _vdt(x),
-           _stream())
+           n_rows, n_cols, F, REDUCE[reduce], *args, _p(bias), _p(x_halo), n_local, int(bool(accumulate)),
+           peer_ptrs, int(peer_rows), it, _vdt(x), _stream())
     return out
 
 

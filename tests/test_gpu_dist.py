@@ -35,7 +35,7 @@ def _graph(n_total, n_edges, world, seed=7):
     return torch.stack([src, dst]), x, gout, w, b
 
 
-def _run_rank(rank, world, port, n_total, n_edges, q):
+def _run_rank(rank, world, port, n_total, n_edges, q, mode="nccl"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -61,10 +61,20 @@ def _run_rank(rank, world, port, n_total, n_edges, q):
         conv.bias.grad = None
         # sharded
         mine = (ei[1] >= lo) & (ei[1] < lo + n_local)
-        shard = pd.ShardedGCNGraph.build(ei[:, mine].to(dev), lo, n_local, n_total)
         xl = x[lo:lo + n_local].to(dev).requires_grad_()
-        out = pd.sharded_gcn_conv(conv, xl, shard)
-        out.backward(gout[lo:lo + n_local].to(dev))
+        if mode == "p2p":
+            from pytorch_geometric_b200 import dist_p2p
+            shard = dist_p2p.PeerShardedGCNGraph.build(ei[:, mine].to(dev), lo, n_local, n_total, 128)
+            for _ in range(2):          # run twice: the second pass exercises the reuse barriers
+                xl.grad = None
+                conv.lin.weight.grad = None
+                conv.bias.grad = None
+                out = dist_p2p.peer_sharded_gcn_conv(conv, xl, shard)
+                out.backward(gout[lo:lo + n_local].to(dev))
+        else:
+            shard = pd.ShardedGCNGraph.build(ei[:, mine].to(dev), lo, n_local, n_total)
+            out = pd.sharded_gcn_conv(conv, xl, shard)
+            out.backward(gout[lo:lo + n_local].to(dev))
         gw = conv.lin.weight.grad.clone()
         if world > 1:
             dist.all_reduce(gw)
@@ -79,11 +89,11 @@ def _run_rank(rank, world, port, n_total, n_edges, q):
         dist.destroy_process_group()
 
 
-def _launch(world):
+def _launch(world, mode="nccl"):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_run_rank, args=(r, world, port, 20000, 300000, q)) for r in range(world)]
+    procs = [ctx.Process(target=_run_rank, args=(r, world, port, 20000, 300000, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in procs]
@@ -100,3 +110,9 @@ def test_sharded_gcn_conv_single_rank_equals_unsharded():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_sharded_gcn_conv_two_ranks_nccl_equals_unsharded():
     _launch(2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_peer_memory_gcn_conv_two_ranks_equals_unsharded():
+    """Halo rows gathered over NVLink peer memory inside the kernel (dist_p2p.py)."""
+    _launch(2, "p2p")
