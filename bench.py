@@ -232,6 +232,10 @@ def run_b200(args):
     dense.set_backend(args.dense)
     if args.gemm_bk:
         ops.set_option("gemm_bk", args.gemm_bk)
+    if args.gemm_mode >= 0:
+        ops.set_option("gemm_mode", args.gemm_mode)
+    if args.gemm_prefetch >= 0:
+        ops.set_option("gemm_prefetch", args.gemm_prefetch)
     torch.manual_seed(1234 + rank)
     conv = GCNConv(F, F, cached=True).to(dev)
     with torch.no_grad():
@@ -456,6 +460,8 @@ def main():
     ap.add_argument("--dense", default="tf32x3", choices=["tf32x3", "cublas"],
                     help="dense transform: hand-written tcgen05 3xTF32 GEMM (fp32-accurate) or strict-fp32 cuBLAS")
     ap.add_argument("--gemm-bk", type=int, default=0, help="k-block width of the tcgen05 GEMM (16 or 32; 0 = library default)")
+    ap.add_argument("--gemm-prefetch", type=int, default=-1, help="TMA L2-prefetch distance of the GEMM in k-blocks")
+    ap.add_argument("--gemm-mode", type=int, default=-1, help="0 = SS-mode GEMM, 1 = TS-mode (A in TMEM); -1 = library default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,

@@ -46,6 +46,12 @@ static int g_spmm_impl = 0;
 int get_option_spmm_impl() { return g_spmm_impl; }
 static int g_gemm_bk = 32;
 int get_option_gemm_bk() { return g_gemm_bk; }
+static int g_gemm_prefetch = 0;
+int get_option_gemm_prefetch() { return g_gemm_prefetch; }
+static int g_gemm_debug = 0;
+int get_option_gemm_debug() { return g_gemm_debug; }
+static int g_gemm_mode = 1;   // TS mode (A operand in TMEM) measured 25 % faster than SS (profiles/r1_summary.md)
+int get_option_gemm_mode() { return g_gemm_mode; }
 static int g_spmm_tune = 0;
 int get_option_spmm_tune() { return g_spmm_tune; }
 
@@ -86,6 +92,20 @@ extern "C" int b200mp_set_option(const char* name, int value) {
     }
     if (strcmp(name, "spmm_tune") == 0) {
         b200mp::g_spmm_tune = value;
+        return B200MP_OK;
+    }
+    if (strcmp(name, "gemm_prefetch") == 0) {
+        if (value < 0 || value > 64) return B200MP_ERR_INVALID_ARG;
+        b200mp::g_gemm_prefetch = value;
+        return B200MP_OK;
+    }
+    if (strcmp(name, "gemm_debug") == 0) {
+        b200mp::g_gemm_debug = value;
+        return B200MP_OK;
+    }
+    if (strcmp(name, "gemm_mode") == 0) {
+        if (value != 0 && value != 1) return B200MP_ERR_INVALID_ARG;
+        b200mp::g_gemm_mode = value;
         return B200MP_OK;
     }
     if (strcmp(name, "gemm_bk") == 0) {

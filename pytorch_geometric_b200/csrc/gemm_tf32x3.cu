@@ -63,6 +63,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// TMA prefetch of one box into L2 (no shared memory, no barrier): issued a few k-blocks ahead so the
+// real load finds its data in L2 instead of paying the HBM latency inside a 2..4 deep smem ring.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -95,6 +102,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 256-bit global store (sm_100+): a thread that owns 8 consecutive fp32 of a row writes one complete
+// 32-byte sector per instruction instead of two half-filled ones.
+__device__ __forceinline__ void stg_v8(float* p, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
 }
 __device__ __forceinline__ float rn_tf32(float a) {
     uint32_t r;
@@ -134,6 +148,9 @@ struct GemmArgs {
     int k_blocks;         // total 32-wide k-blocks
     int k_blocks_per_split;
     int n_splits;
+    int prefetch;         // L2 prefetch distance in k-blocks (0 = off)
+    int debug;            // timing experiments only (results are WRONG when non-zero): bit0 = skip the hi/lo split,
+                          // bit1 = issue only the hi*hi product, bit2 = epilogue skips the global stores
 };
 
 // A_MN / B_MN: operand is MN-major (stored row-major as [K, MN]); B_PRE: B arrives pre-split
@@ -202,6 +219,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 const int kb0 = split * args.k_blocks_per_split;
                 const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    if (args.prefetch > 0) {
+                        // streaming operands (A always, B when it is not the pre-split weight) `prefetch` k-blocks ahead
+                        int pk = kb + args.prefetch, pm0 = m0;
+                        bool ok = pk < kb1;
+                        if (!ok && args.n_splits == 1 && w + static_cast<int>(gridDim.x) < n_work) {
+                            pk = kb0 + (pk - kb1);                                  // wraps into this CTA's next tile
+                            pm0 = ((w + static_cast<int>(gridDim.x)) / args.n_tiles_n) * kBM;
+                            ok = pk < kb1;
+                        }
+                        if (ok) {
+                            if (A_MN) {
+#pragma unroll
+                                for (int s = 0; s < kBM / 32; ++s) tma_prefetch_2d(&tmap_a, pm0 + 32 * s, pk * kBK);
+                            } else {
+                                tma_prefetch_2d(&tmap_a, pk * kBK, pm0);
+                            }
+                            if (!B_PRE && B_MN) {
+#pragma unroll
+                                for (int s = 0; s < BN / 32; ++s) tma_prefetch_2d(&tmap_b_hi, n0 + 32 * s, pk * kBK);
+                            }
+                        }
+                    }
                     bar_wait(bar_empty(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * kStageBytes;
                     const uint32_t sb_hi = sa + 2 * kABytes;
@@ -258,9 +297,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         const uint64_t a_lo = smem_desc<A_MN, BK>(sa_lo + ao, kSlab);
                         const uint64_t b_hi = smem_desc<B_MN, BK>(sb_hi + bo, kSlab);
                         const uint64_t b_lo = smem_desc<B_MN, BK>(sb_lo + bo, kSlab);
-                        umma_tf32(d, a_lo, b_hi, kIdesc, accumulate);     // small terms first
-                        umma_tf32(d, a_hi, b_lo, kIdesc, 1u);
-                        umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                        if (!(args.debug & 2)) {
+                            umma_tf32(d, a_lo, b_hi, kIdesc, accumulate);     // small terms first
+                            umma_tf32(d, a_hi, b_lo, kIdesc, 1u);
+                            umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                        } else {
+                            umma_tf32(d, a_hi, b_hi, kIdesc, accumulate);
+                        }
                         accumulate = 1u;
                     }
                     umma_commit(bar_empty(stage));                        // frees the smem stage when the MMAs retire
@@ -291,8 +334,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         *reinterpret_cast<float4*>(lo + off) = l;
                     }
                 };
-                split_buf(sa, sa + kABytes, kABytes);
-                if (!B_PRE) split_buf(sa + 2 * kABytes, sa + 2 * kABytes + kBBytes, kBBytes);
+                if (!(args.debug & 1)) {
+                    split_buf(sa, sa + kABytes, kABytes);
+                    if (!B_PRE) split_buf(sa + 2 * kABytes, sa + 2 * kABytes + kBBytes, kBBytes);
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async (MMA) reads
                 bar_arrive(bar_split(stage));
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -316,11 +361,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c0), r);
-                if (row < args.m) {
+                if (row < args.m && !(args.debug & 4)) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4*>(crow + c0 + i) =
-                            make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                    for (int i = 0; i < 32; i += 8) stg_v8(crow + c0 + i, r + i);   // 256-bit stores: one full 32 B sector each
                 }
             }
             tc_fence_before();
@@ -413,17 +456,37 @@ static bool ok16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 }  // namespace b200mp
 
+#include "gemm_tf32x3_ts.cuh"
+
 using namespace b200mp;
 
 namespace b200mp {
 int get_option_gemm_bk();   // 16 or 32 (b200mp_set_option("gemm_bk", ...)); default = measured best
+int get_option_gemm_mode(); // 0 = SS (A and B in shared memory), 1 = TS (A operand in tensor memory)
+int get_option_gemm_debug();
+int get_option_gemm_prefetch(); // L2 prefetch distance in k-blocks for the streaming operands (0 = off)
 
 static bool width_ok(int64_t w) { return w == 64 || w == 128 || (w > 0 && w % 256 == 0); }
+
+// TS path (A in TMEM): y[M, n_out] = a[M, k_red] . B, B pre-split, K-major or MN-major
+static int run_ts(const float* a, const float* b_hi, const float* b_lo, float* c, int64_t m, int64_t n_out, int64_t k_red,
+                  bool b_mn, int64_t b_rows, int64_t b_cols, cudaStream_t s) {
+    CUtensorMap ta, tbh, tbl, tc;
+    int rc;
+    if ((rc = make_map(&tc, c, m, n_out, n_out, false, 32, 32))) return rc;      // output boxes [32 rows x 32 cols]
+    if ((rc = make_map(&ta, a, m, k_red, k_red, false, 32, kBM))) return rc;
+    if ((rc = make_map(&tbh, b_hi, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
+    if ((rc = make_map(&tbl, b_lo, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
+    const int kb = static_cast<int>(k_red / 32);
+    GemmArgs args{c, m, n_out, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n_out / kTsBN), kb, kb, 1, get_option_gemm_prefetch(), get_option_gemm_debug()};
+    return b_mn ? launch_gemm_ts<true>(ta, tbh, tbl, tc, args, s) : launch_gemm_ts<false>(ta, tbh, tbl, tc, args, s);
+}
 
 // y[M,N] = x[M,K] . w[N,K]^T
 template <int BK>
 static int run_forward(const float* x, const float* w_hi, const float* w_lo, float* y, int64_t m, int64_t n, int64_t k,
                        cudaStream_t s) {
+    if (get_option_gemm_mode() == 1 && n % kTsBN == 0) return run_ts(x, w_hi, w_lo, y, m, n, k, false, n, k, s);
     const int bn = n >= 256 ? 256 : static_cast<int>(n);
     CUtensorMap ta, tbh, tbl;
     int rc;
@@ -431,7 +494,7 @@ static int run_forward(const float* x, const float* w_hi, const float* w_lo, flo
     if ((rc = make_map(&tbh, w_hi, n, k, k, false, BK, bn))) return rc;
     if ((rc = make_map(&tbl, w_lo, n, k, k, false, BK, bn))) return rc;
     const int kb = static_cast<int>(k / BK);
-    GemmArgs a{y, m, n, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n / bn), kb, kb, 1};
+    GemmArgs a{y, m, n, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n / bn), kb, kb, 1, get_option_gemm_prefetch(), get_option_gemm_debug()};
     if (bn == 256) return launch_gemm<256, BK, false, false, true>(ta, tbh, tbl, a, s);
     if (bn == 128) return launch_gemm<128, BK, false, false, true>(ta, tbh, tbl, a, s);
     return launch_gemm<64, BK, false, false, true>(ta, tbh, tbl, a, s);
@@ -440,6 +503,7 @@ static int run_forward(const float* x, const float* w_hi, const float* w_lo, flo
 template <int BK>
 static int run_grad_input(const float* g, const float* w_hi, const float* w_lo, float* gx, int64_t m, int64_t n, int64_t k,
                           cudaStream_t s) {
+    if (get_option_gemm_mode() == 1 && k % kTsBN == 0) return run_ts(g, w_hi, w_lo, gx, m, k, n, true, n, k, s);
     const int bn = k >= 256 ? 256 : static_cast<int>(k);
     CUtensorMap ta, tbh, tbl;
     int rc;
@@ -447,7 +511,7 @@ static int run_grad_input(const float* g, const float* w_hi, const float* w_lo, 
     if ((rc = make_map(&tbh, w_hi, n, k, k, true, BK, 0))) return rc;
     if ((rc = make_map(&tbl, w_lo, n, k, k, true, BK, 0))) return rc;
     const int kb = static_cast<int>(n / BK);
-    GemmArgs a{gx, m, k, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(k / bn), kb, kb, 1};
+    GemmArgs a{gx, m, k, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(k / bn), kb, kb, 1, get_option_gemm_prefetch(), get_option_gemm_debug()};
     if (bn == 256) return launch_gemm<256, BK, false, true, true>(ta, tbh, tbl, a, s);
     if (bn == 128) return launch_gemm<128, BK, false, true, true>(ta, tbh, tbl, a, s);
     return launch_gemm<64, BK, false, true, true>(ta, tbh, tbl, a, s);
@@ -474,7 +538,7 @@ static int run_grad_weight(const float* g, const float* x, float* gw, int64_t m,
     if ((rc = make_map(&ta, g, m, n, n, true, BK, 0))) return rc;   // A[m' = n-index, k' = row]: stored [K' rows][M' cols]
     if ((rc = make_map(&tb, x, m, k, k, true, BK, 0))) return rc;
     GemmArgs a{static_cast<float*>(workspace), n, k, static_cast<int>(n / kBM), static_cast<int>(k / bn),
-               static_cast<int>(kblocks), kbps, splits};
+               static_cast<int>(kblocks), kbps, splits, get_option_gemm_prefetch(), get_option_gemm_debug()};
     if (bn == 256) rc = launch_gemm<256, BK, true, true, false>(ta, tb, tb, a, s);
     else if (bn == 128) rc = launch_gemm<128, BK, true, true, false>(ta, tb, tb, a, s);
     else rc = launch_gemm<64, BK, true, true, false>(ta, tb, tb, a, s);

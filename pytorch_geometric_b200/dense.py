@@ -19,6 +19,8 @@ from . import ops
 from ._lib import check, lib
 
 _BACKEND = "tf32x3"
+DEFAULT_GEMM_MODE = 1   # library default of b200mp_set_option("gemm_mode"): 0 = SS, 1 = TS (A operand in TMEM)
+DEFAULT_GEMM_PREFETCH = 0   # library default of b200mp_set_option("gemm_prefetch") (k-blocks ahead, 0 = off)
 
 
 def set_backend(name: str) -> None:

@@ -12,6 +12,7 @@ from pytorch_geometric_b200 import dense  # noqa: E402
 from pytorch_geometric_b200.nn import GCNConv  # noqa: E402
 
 DEV = "cuda"
+DEFAULT_GEMM_MODE = dense.DEFAULT_GEMM_MODE
 
 
 def _check(got, ref64, scale64, tol=1e-5):
@@ -20,12 +21,18 @@ def _check(got, ref64, scale64, tol=1e-5):
     assert (err <= bound).all(), f"max err/scale {float((err / (scale64 + 1e-30)).max()):.3e}"
 
 
-@pytest.fixture(params=[32, 16], ids=["bk32", "bk16"])
+@pytest.fixture(params=["ss-bk32", "ss-bk16", "ts"])
 def gemm_bk(request):
+    """Kernel variants: SS mode (both operands in shared memory) with 2 x 96 KB or 4 x 48 KB stages,
+    and TS mode (A operand in tensor memory)."""
     from pytorch_geometric_b200 import ops
-    ops.set_option("gemm_bk", request.param)      # k-block width: 2 x 96 KB or 4 x 48 KB pipeline stages
+    ops.set_option("gemm_mode", 1 if request.param == "ts" else 0)
+    ops.set_option("gemm_bk", 16 if request.param == "ss-bk16" else 32)
+    ops.set_option("gemm_prefetch", 0 if request.param == "ss-bk32" else 8)     # TMA L2 prefetch distance
     yield request.param
     ops.set_option("gemm_bk", 32)
+    ops.set_option("gemm_prefetch", dense.DEFAULT_GEMM_PREFETCH)
+    ops.set_option("gemm_mode", DEFAULT_GEMM_MODE)
 
 
 @pytest.mark.parametrize("m", [1, 127, 128, 129, 1000, 20011])
