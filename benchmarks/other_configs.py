@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Timing of the non-headline BASELINE.json configs on one B200 (parity for these is in tests/;
+they are not bench.py lines).  Prints one JSON object per config.
+
+  config 2: 3-layer SAGEConv(mean), synthetic power-law 10 M nodes / 100 M edges, h = 256, fp32
+  config 3: GATConv 8 heads x 16, ogbn-products-shaped synthetic (2.4 M nodes / 123 M edges), bf16 features
+  config 5: RGCNConv 4 relations, 5 M nodes / 50 M edges (single GPU here), h = 64, fp32
+
+    python benchmarks/other_configs.py [--configs 2,3,5] [--steps 3]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import synth_graph  # noqa: E402
+
+
+def timed(fn, steps):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="2,3,5")
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args()
+    from pytorch_geometric_b200 import functional as Fn
+    from pytorch_geometric_b200.graph import CSRGraph
+    from pytorch_geometric_b200.nn import GATConv, RGCNConv, SAGEConv
+    dev = torch.device("cuda", 0)
+    todo = {int(c) for c in args.configs.split(",")}
+
+    if 2 in todo:
+        N, E, F = 10_000_000, 100_000_000, 256
+        ei = synth_graph(N, E, 2, dev)
+        g = CSRGraph(ei[0], ei[1], N, N)
+        g.build_transpose()
+        del ei
+        convs = torch.nn.ModuleList([SAGEConv(F, F) for _ in range(3)]).to(dev)
+        x = torch.randn(N, F, device=dev)
+        gout = torch.randn(N, F, device=dev)
+
+        def step():
+            for c in convs:
+                c.zero_grad(set_to_none=True)
+            h = x
+            for i, c in enumerate(convs):
+                h = c(h, g)
+                if i < 2:
+                    h = h.relu_()
+            h.backward(gout)
+
+        ms = timed(step, args.steps)
+        print(json.dumps({"config": 2, "what": "3-layer SAGEConv(mean) fwd+bwd, N=10M, E=100M, h=256, fp32",
+                          "ms_per_step": ms, "edge_layers_per_s": 3 * E / (ms * 1e-3)}))
+        del g, convs, x, gout
+        torch.cuda.empty_cache()
+
+    if 3 in todo:
+        N, E, H, C = 2_400_000, 123_000_000, 8, 16
+        ei = synth_graph(N, E, 3, dev)
+        conv = GATConv(128, C, heads=H).to(dev)
+        g = conv.graph_for(ei, N)                      # remove + add self loops, CSR
+        g.build_transpose()
+        _ = g.t2csr
+        del ei
+        deg = g.in_degree()
+        xh = torch.randn(N, H * C, device=dev).bfloat16()
+        a_s = torch.randn(N, H, device=dev)
+        a_d = torch.randn(N, H, device=dev)
+        ms_f = timed(lambda: Fn.gat_attention(g, xh, a_s, a_d, H, C, 0.2), args.steps)
+        xh32 = xh.float().requires_grad_()
+        a_s.requires_grad_()
+        a_d.requires_grad_()
+        gout = torch.randn(N, H * C, device=dev)
+
+        def step():
+            xh32.grad = a_s.grad = a_d.grad = None
+            Fn.gat_attention(g, xh32, a_s, a_d, H, C, 0.2).backward(gout)
+
+        ms_fb = timed(step, args.steps)
+        Ep = g.num_edges
+        bytes_fwd = Ep * (H * C * 2 + H * 4 + 4) + N * (H * C * 2 + 3 * H * 4)
+        print(json.dumps({"config": 3, "what": "fused GAT attention+aggregation, N=2.4M, E=123M (+N loops), 8x16",
+                          "max_in_degree": int(deg.max()), "fwd_ms_bf16": ms_f,
+                          "fwd_algorithmic_GBps": bytes_fwd / (ms_f * 1e-3) / 1e9, "fwd_bwd_ms_fp32": ms_fb,
+                          "edges_per_s_fwd_bwd": E / (ms_fb * 1e-3)}))
+        del g, xh, xh32, a_s, a_d, gout
+        torch.cuda.empty_cache()
+
+    if 5 in todo:
+        N, E, R, F = 5_000_000, 50_000_000, 4, 64
+        ei = synth_graph(N, E, 5, dev)
+        et = torch.randint(0, R, (E, ), device=dev)
+        conv = RGCNConv(F, F, R).to(dev)
+        g = conv.relation_graph(ei, et, N)
+        g.build_transpose()
+        del ei, et
+        x = torch.randn(N, F, device=dev).requires_grad_()
+        gout = torch.randn(N, F, device=dev)
+
+        def step():
+            x.grad = None
+            conv.zero_grad(set_to_none=True)
+            conv(x, g).backward(gout)
+
+        ms = timed(step, args.steps)
+        print(json.dumps({"config": 5, "what": "RGCNConv(mean) 4 relations fwd+bwd, N=5M, E=50M, h=64, fp32, 1 GPU",
+                          "ms_per_step": ms, "edges_per_s": E / (ms * 1e-3)}))
+
+
+if __name__ == "__main__":
+    main()

@@ -215,24 +215,34 @@ int b200mp_softmax_csr_backward(const void* ptr, const float* out, const float* 
  * xh: [n_src, heads*chan] val_dtype; a_src [n_src, heads], a_dst [n_rows, heads] fp32;
  * out: [n_rows, heads*chan] val_dtype; row_max/row_den [n_rows, heads] fp32 (saved for backward);
  * alpha_out (nullable) [n_edges, heads] fp32 in CSR order. */
-int b200mp_gat_fused_csr(const void* rowptr, const void* col, const void* xh, const float* a_src,
-                         const float* a_dst, void* out, float* row_max, float* row_den,
-                         float* alpha_out, int64_t n_rows, int64_t heads, int64_t chan,
-                         float slope, int idx_dtype, int val_dtype, void* stream);
-/* Backward of b200mp_gat_fused_csr in two sweeps, attention recomputed from row_max/row_den:
- *  destination sweep (rowptr/col): grad_pre[e,h] (CSR order, scratch [n_edges, heads]) and
- *      grad_a_dst[i,h];
+int b200mp_gat_fused_csr(const void* rowptr, const void* col, const void* dst_of_edge, const void* xh,
+                         const float* a_src, const float* a_dst, void* out, float* row_max,
+                         float* row_den, float* alpha_out, int64_t n_rows, int64_t n_edges,
+                         int64_t heads, int64_t chan, float slope, const int64_t* long_rows,
+                         const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks, int64_t chunk,
+                         float* part_acc, float* part_ms, int idx_dtype, int val_dtype, void* stream);
+/* (dst_of_edge = ptr2index(rowptr), only needed with alpha_out.  Hub rows: pass the long-row plan of
+ * b200mp_csr_plan_* plus part_acc [n_chunks, heads*chan] and part_ms [n_chunks, heads, 2] fp32; every
+ * chunk keeps an online-softmax state that is merged with exp(m_c - M) rescaling.)
+ *
+ * Backward of b200mp_gat_fused_csr, attention recomputed from row_max/row_den:
+ *  row dots    rowdot[i,h] = <g[i,h,:], out[i,h,:]>               (scratch [n_rows, heads])
+ *  edge sweep  grad_pre[e,h] (CSR order, scratch [n_edges, heads]) -- one thread per (edge, head), so
+ *              no row is walked serially -- and grad_a_dst[i,h] = its (chunked) segmented sum
+ *              (partials: n_chunks * heads fp32 when the plan is given)
  *  source sweep (rowptr_t/col_t, t2csr[e] = CSR slot of transposed slot e): grad_xh[j,h,:] (the
- *      message term only; the a_src/a_dst terms flow back through the caller's (xh*att).sum(-1))
- *      and grad_a_src[j,h]. */
-int b200mp_gat_fused_csr_backward(const void* rowptr, const void* col, const void* rowptr_t,
-                                  const void* col_t, const void* t2csr, const void* xh,
-                                  const float* a_src, const float* a_dst, const float* row_max,
-                                  const float* row_den, const void* out, const void* grad_out,
-                                  float* grad_pre, void* grad_xh, float* grad_a_src,
-                                  float* grad_a_dst, int64_t n_rows, int64_t n_src, int64_t heads,
-                                  int64_t chan, float slope, int idx_dtype, int val_dtype,
-                                  void* stream);
+ *              message term only; the a_src/a_dst terms flow back through the caller's
+ *              (xh*att).sum(-1)) and grad_a_src[j,h]. */
+int b200mp_gat_fused_csr_backward(const void* rowptr, const void* col, const void* dst_of_edge,
+                                  const void* rowptr_t, const void* col_t, const void* t2csr,
+                                  const void* xh, const float* a_src, const float* a_dst,
+                                  const float* row_max, const float* row_den, const void* out,
+                                  const void* grad_out, float* grad_pre, float* rowdot, void* grad_xh,
+                                  float* grad_a_src, float* grad_a_dst, int64_t n_rows, int64_t n_src,
+                                  int64_t n_edges, int64_t heads, int64_t chan, float slope,
+                                  const int64_t* long_rows, const int64_t* chunk_ptr,
+                                  int64_t n_long_rows, int64_t n_chunks, int64_t chunk, float* partials,
+                                  int idx_dtype, int val_dtype, void* stream);
 
 /* ------------------------------------------------------------------ dense transform on tensor cores
  * fp32-accurate 3xTF32 GEMMs (tcgen05 + TMEM + TMA, csrc/gemm_tf32x3.cu) for the layer's

@@ -52,8 +52,9 @@ _SIGS = {
     "b200mp_gather_rows": (_INT, [_P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
     "b200mp_softmax_csr": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P]),
     "b200mp_softmax_csr_backward": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _INT, _P]),
-    "b200mp_gat_fused_csr": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _F, _INT, _INT, _P]),
-    "b200mp_gat_fused_csr_backward": (_INT, [_P] * 16 + [_I64, _I64, _I64, _I64, _F, _INT, _INT, _P]),
+    "b200mp_gat_fused_csr": (_INT, [_P] * 10 + [_I64, _I64, _I64, _I64, _F, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _INT, _P]),
+    "b200mp_gat_fused_csr_backward": (_INT, [_P] * 18 + [_I64, _I64, _I64, _I64, _I64, _F, _P, _P, _I64, _I64, _I64, _P,
+                                              _INT, _INT, _P]),
 }
 
 _lib = None

@@ -420,6 +420,9 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     const int box_cols = mn ? 32 : bk;
     if (mn) box_rows = bk;
     EncodeTiledFn fn = encode_fn();
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context.  On a fresh thread (the
+    // autograd engine's backward thread) no runtime call may have bound the primary context yet.
+    cudaFree(nullptr);
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
         return B200MP_ERR_CUDA;

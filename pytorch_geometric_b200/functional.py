@@ -171,7 +171,8 @@ class _GATFused(torch.autograd.Function):
     def forward(ctx, xh: Tensor, a_src: Tensor, a_dst: Tensor, graph: CSRGraph, heads: int, chan: int, slope: float,
                 want_alpha: bool):
         out, row_max, row_den, alpha = ops.gat_fused_csr(graph.rowptr, graph.col, xh, a_src, a_dst, heads, chan,
-                                                         slope, want_alpha)
+                                                         slope, want_alpha, plan=graph.plan,
+                                                         dst_of_edge=graph.dst_csr if want_alpha else None)
         ctx.graph, ctx.dims = graph, (heads, chan, slope)
         ctx.save_for_backward(xh, a_src, a_dst, row_max, row_den, out)
         if alpha is None:
@@ -185,9 +186,10 @@ class _GATFused(torch.autograd.Function):
         graph = ctx.graph
         heads, chan, slope = ctx.dims
         graph.build_transpose()
-        gxh, gas, gad = ops.gat_fused_csr_backward(graph.rowptr, graph.col, graph.rowptr_t, graph.col_t, graph.t2csr,
-                                                   xh, a_src.float().contiguous(), a_dst.float().contiguous(),
-                                                   row_max, row_den, out, grad_out, heads, chan, slope)
+        gxh, gas, gad = ops.gat_fused_csr_backward(graph.rowptr, graph.col, graph.dst_csr, graph.rowptr_t, graph.col_t,
+                                                   graph.t2csr, xh, a_src.float().contiguous(),
+                                                   a_dst.float().contiguous(), row_max, row_den, out, grad_out,
+                                                   heads, chan, slope, plan=graph.plan)
         return gxh, gas.to(a_src.dtype), gad.to(a_dst.dtype), None, None, None, None, None
 
 

@@ -380,8 +380,17 @@ def softmax_csr_backward(out: Tensor, grad_out: Tensor, ptr: Tensor) -> Tensor:
     return g.view(out.shape)
 
 
+def _plan_args(plan, feat: int, device):
+    """(long_rows, chunk_ptr, n_long, n_chunks, chunk, partials[n_chunks*feat]) for the C ABI."""
+    if plan is None or not plan.n_long:
+        return (None, None, 0, 0, 0, None), None
+    part = plan.partials(feat, device)
+    return (_p(plan.long_rows), _p(plan.chunk_ptr), plan.n_long, plan.n_chunks, plan.chunk, _p(part)), part
+
+
 def gat_fused_csr(rowptr: Tensor, col: Tensor, xh: Tensor, a_src: Tensor, a_dst: Tensor, heads: int, chan: int,
-                  slope: float, want_alpha: bool = False):
+                  slope: float, want_alpha: bool = False, plan: Optional["LongRowPlan"] = None,
+                  dst_of_edge: Optional[Tensor] = None):
     """Fused GAT forward: returns (out [n_rows, H*C], row_max, row_den, alpha or None)."""
     _cuda(rowptr, col, xh, a_src, a_dst)
     it = _same_idx(rowptr, col)
@@ -392,28 +401,33 @@ def gat_fused_csr(rowptr: Tensor, col: Tensor, xh: Tensor, a_src: Tensor, a_dst:
     row_max = torch.empty((n_rows, heads), dtype=torch.float32, device=xh.device)
     row_den = torch.empty_like(row_max)
     alpha = torch.empty((col.numel(), heads), dtype=torch.float32, device=xh.device) if want_alpha else None
-    check(lib().b200mp_gat_fused_csr(_p(rowptr), _p(col), _p(xh), _p(a_src), _p(a_dst), _p(out), _p(row_max),
-                                     _p(row_den), _p(alpha), n_rows, heads, chan, float(slope), it, _vdt(xh),
-                                     _stream()), "gat_fused_csr")
+    if want_alpha and dst_of_edge is None:
+        dst_of_edge = ptr2index(rowptr, col.numel())
+    pargs, _part = _plan_args(plan, heads * chan, xh.device)
+    part_ms = torch.empty(plan.n_chunks * heads * 2, dtype=torch.float32, device=xh.device) if pargs[2] else None
+    _timed("gat_fused_csr", 2 if pargs[2] else 1, lib().b200mp_gat_fused_csr, _p(rowptr), _p(col), _p(dst_of_edge), _p(xh),
+           _p(a_src), _p(a_dst), _p(out), _p(row_max), _p(row_den), _p(alpha), n_rows, col.numel(), heads, chan,
+           float(slope), *pargs, _p(part_ms), it, _vdt(xh), _stream())
     return out, row_max, row_den, alpha
 
 
-def gat_fused_csr_backward(rowptr, col, rowptr_t, col_t, t2csr, xh, a_src, a_dst, row_max, row_den, out, grad_out,
-                           heads: int, chan: int, slope: float):
+def gat_fused_csr_backward(rowptr, col, dst_of_edge, rowptr_t, col_t, t2csr, xh, a_src, a_dst, row_max, row_den, out,
+                           grad_out, heads: int, chan: int, slope: float, plan: Optional["LongRowPlan"] = None):
     """Returns (grad_xh [n_src, H*C], grad_a_src [n_src, H], grad_a_dst [n_rows, H])."""
-    _cuda(rowptr, col, rowptr_t, col_t, t2csr, xh, grad_out)
-    it = _same_idx(rowptr, col, rowptr_t, col_t, t2csr)
+    _cuda(rowptr, col, dst_of_edge, rowptr_t, col_t, t2csr, xh, grad_out)
+    it = _same_idx(rowptr, col, dst_of_edge, rowptr_t, col_t, t2csr)
     grad_out = grad_out.contiguous()
     n_rows, n_src = rowptr.numel() - 1, rowptr_t.numel() - 1
     grad_pre = torch.empty((col.numel(), heads), dtype=torch.float32, device=xh.device)
+    rowdot = torch.empty((n_rows, heads), dtype=torch.float32, device=xh.device)
     gxh = torch.empty_like(xh)
     gas = torch.empty((n_src, heads), dtype=torch.float32, device=xh.device)
     gad = torch.empty((n_rows, heads), dtype=torch.float32, device=xh.device)
-    check(lib().b200mp_gat_fused_csr_backward(_p(rowptr), _p(col), _p(rowptr_t), _p(col_t), _p(t2csr), _p(xh),
-                                              _p(a_src), _p(a_dst), _p(row_max), _p(row_den), _p(out),
-                                              _p(grad_out), _p(grad_pre), _p(gxh), _p(gas), _p(gad), n_rows, n_src,
-                                              heads, chan, float(slope), it, _vdt(xh), _stream()),
-          "gat_fused_csr_backward")
+    pargs, _part = _plan_args(plan, heads, xh.device)
+    _timed("gat_fused_csr_backward", 5, lib().b200mp_gat_fused_csr_backward, _p(rowptr), _p(col), _p(dst_of_edge),
+           _p(rowptr_t), _p(col_t), _p(t2csr), _p(xh), _p(a_src), _p(a_dst), _p(row_max), _p(row_den), _p(out),
+           _p(grad_out), _p(grad_pre), _p(rowdot), _p(gxh), _p(gas), _p(gad), n_rows, n_src, col.numel(), heads, chan,
+           float(slope), *pargs, it, _vdt(xh), _stream())
     return gxh, gas, gad
 
 

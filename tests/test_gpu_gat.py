@@ -48,9 +48,10 @@ def test_gat_conv_golden_forward_backward():
     assert_close(npy(conv.att_dst.grad), g["gatt_dst"], rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("chunk", [512, 16])   # 16: hub rows go through the chunked online-softmax + merge path
 @pytest.mark.parametrize("H,C,dtype", [(8, 16, torch.float32), (8, 16, torch.bfloat16), (4, 3, torch.float32),
                                        (1, 64, torch.float32), (2, 128, torch.float32), (8, 4, torch.bfloat16)])
-def test_gat_attention_vs_oracle(H, C, dtype):
+def test_gat_attention_vs_oracle(H, C, dtype, chunk):
     rng = np.random.default_rng(H * 100 + C)
     N, E = 500, 8000
     src = rng.integers(0, N, size=E)
@@ -60,7 +61,9 @@ def test_gat_attention_vs_oracle(H, C, dtype):
     att_s = rng.standard_normal((H, C)).astype(np.float32) * 0.5
     att_d = rng.standard_normal((H, C)).astype(np.float32) * 0.5
     ref_out, ref_alpha, r2, c2 = O.gat_attention(xh, att_s, att_d, src, dst, 0.2, add_self_loops=True)
-    g = CSRGraph(cu(r2), cu(c2), N, N)
+    g = CSRGraph(cu(r2), cu(c2), N, N, chunk=chunk)
+    if chunk == 16:
+        assert g.plan.n_long > 0
     a_src = (xh * att_s).sum(-1).astype(np.float32)
     a_dst = (xh * att_d).sum(-1).astype(np.float32)
     out, alpha = Fn.gat_attention(g, cu(xh.reshape(N, H * C)).to(dtype), cu(a_src), cu(a_dst), H, C, 0.2, True)
@@ -79,7 +82,8 @@ def test_gat_backward_matches_autograd_of_unfused_formula():
     N, E, H, C = 300, 4000, 8, 16
     src = torch.randint(0, N, (E, ), device=DEV)
     dst = (torch.rand(E, device=DEV) ** 2 * (N - 1)).long()
-    g = CSRGraph(src, dst, N, N)
+    g = CSRGraph(src, dst, N, N, chunk=8)          # most rows are "hubs": chunked forward + chunked grad_a_dst
+    assert g.plan.n_long > 0
     xh = torch.randn(N, H * C, device=DEV, requires_grad=True)
     a_s = torch.randn(N, H, device=DEV, requires_grad=True)
     a_d = torch.randn(N, H, device=DEV, requires_grad=True)
