@@ -6,7 +6,10 @@ they are not bench.py lines).  Prints one JSON object per config.
   config 3: GATConv 8 heads x 16, ogbn-products-shaped synthetic (2.4 M nodes / 123 M edges), bf16 features
   config 5: RGCNConv 4 relations, 5 M nodes / 50 M edges (single GPU here), h = 64, fp32
 
-    python benchmarks/other_configs.py [--configs 2,3,5] [--steps 3]
+  config 6: SURVEY section 8(f) rank 1 -- PNA-style [mean, min, max, std] multi-aggregation on the headline graph
+            (10 M nodes / 100 M edges, F = 256, fp32): ONE sweep (csrc/multi_aggr.cu) vs one pass per aggregation
+
+    python benchmarks/other_configs.py [--configs 2,3,5,6] [--steps 3]
 """
 import argparse
 import json
@@ -100,6 +103,67 @@ def main():
                           "fwd_algorithmic_GBps": bytes_fwd / (ms_f * 1e-3) / 1e9, "fwd_bwd_ms_fp32": ms_fb,
                           "edges_per_s_fwd_bwd": E / (ms_fb * 1e-3)}))
         del g, xh, xh32, a_s, a_d, gout
+        torch.cuda.empty_cache()
+
+    if 6 in todo:
+        N, E, F = 10_000_000, 100_000_000, 256
+        ei = synth_graph(N, E, 2, dev)
+        g = CSRGraph(ei[0], ei[1], N, N)
+        g.build_transpose()
+        del ei
+        x = torch.randn(N, F, device=dev)
+        aggrs = ["mean", "min", "max", "std"]
+        ms_fused = timed(lambda: Fn.multi_aggregate(g, x, aggrs), args.steps)
+
+        def separate():
+            mean = Fn.aggregate(g, x, "mean")
+            mn = Fn.aggregate(g, x, "min")
+            mx = Fn.aggregate(g, x, "max")
+            sq = Fn.aggregate(g, x * x, "mean")
+            return mean, mn, mx, (sq - mean * mean).clamp_(min=1e-5).sqrt_()
+
+        ms_sep = timed(separate, args.steps)
+        xg = x.clone().requires_grad_()
+        gouts = [torch.randn(N, F, device=dev) for _ in aggrs]
+
+        def step():
+            xg.grad = None
+            torch.autograd.backward(Fn.multi_aggregate(g, xg, aggrs), gouts)
+
+        ms_fb = timed(step, args.steps)
+        bytes_fwd = E * (F * 4 + 4) + N * F * 4 * len(aggrs) + (N + 1) * 4
+        res = {"config": 6, "what": "multi-aggregation [mean,min,max,std], N=10M, E=100M, F=256, fp32",
+               "fused_fwd_ms": ms_fused, "separate_fwd_ms": ms_sep,
+               "fused_fwd_algorithmic_GBps": bytes_fwd / (ms_fused * 1e-3) / 1e9, "fused_fwd_bwd_ms": ms_fb}
+        del x, xg, gouts
+        torch.cuda.empty_cache()
+        # segment form (what PNAConv / MultiAggregation see): materialised messages [E, 64] sorted by destination
+        Fm = 64
+        msg = torch.randn(E, Fm, device=dev)
+        where = (g.rowptr, g.dst_csr, g.plan)
+        ms_seg = timed(lambda: Fn.multi_aggregate(where, msg, aggrs), args.steps)
+
+        def separate_seg():
+            mean = Fn.segment(msg, g.rowptr, "mean")
+            mn = Fn.segment(msg, g.rowptr, "min")
+            mx = Fn.segment(msg, g.rowptr, "max")
+            sq = Fn.segment(msg * msg, g.rowptr, "mean")
+            return mean, mn, mx, (sq - mean * mean).clamp_(min=1e-5).sqrt_()
+
+        ms_seg_sep = timed(separate_seg, args.steps)
+        mg = msg.clone().requires_grad_()
+        gouts = [torch.randn(N, Fm, device=dev) for _ in aggrs]
+
+        def step_seg():
+            mg.grad = None
+            torch.autograd.backward(Fn.multi_aggregate(where, mg, aggrs), gouts)
+
+        ms_seg_fb = timed(step_seg, args.steps)
+        res.update(segment_F=Fm, segment_fused_fwd_ms=ms_seg, segment_separate_fwd_ms=ms_seg_sep,
+                   segment_fused_fwd_algorithmic_GBps=(E * Fm * 4 + N * Fm * 4 * len(aggrs) + (N + 1) * 4) / (ms_seg * 1e-3) / 1e9,
+                   segment_fused_fwd_bwd_ms=ms_seg_fb)
+        print(json.dumps(res))
+        del g, msg, mg, gouts
         torch.cuda.empty_cache()
 
     if 5 in todo:

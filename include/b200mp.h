@@ -154,9 +154,12 @@ int b200mp_spmm_csr(const void* rowptr, const void* col, const float* val, const
 
 /* Segmented reduce without gather: out[i,:] = REDUCE_{e in [ptr[i], ptr[i+1])} src[e,:].
  * Replaces utils/_segment.py:11-50 (torch._segment_reduce / torch_scatter.segment_csr) and the
- * sorted-index case of utils/_scatter.py:14-138.  Same empty-segment and +-inf -> 0 rules. */
+ * sorted-index case of utils/_scatter.py:14-138.  Same empty-segment and +-inf -> 0 rules.
+ * Long segments (hub destinations): optional long-row plan as in b200mp_spmm_csr (n_long_rows = 0: none). */
 int b200mp_segment_csr(const void* ptr, const void* src, void* out, int64_t n_rows, int64_t n_src,
-                       int64_t feat, int reduce, int idx_dtype, int val_dtype, void* stream);
+                       int64_t feat, int reduce, const int64_t* long_rows, const int64_t* chunk_ptr,
+                       int64_t n_long_rows, int64_t n_chunks, int64_t chunk, float* partials,
+                       int idx_dtype, int val_dtype, void* stream);
 
 /* Backward of min/max aggregation (ATen scatter_reduce rule: the gradient is split evenly among
  * tied extrema, and the zero-initialised output counts as one more tie when the extremum is
@@ -205,6 +208,53 @@ int b200mp_softmax_csr(const void* ptr, const float* src, float* out, int64_t n_
 int b200mp_softmax_csr_backward(const void* ptr, const float* out, const float* grad_out,
                                 float* grad_src, int64_t n_rows, int64_t n_src, int64_t heads,
                                 int idx_dtype, void* stream);
+/* Edge-parallel pieces of the hub-safe segment softmax (groups longer than the long-row chunk): with
+ * d = dst_of_edge[e], row [n_rows, heads] fp32,
+ *   op 0: out = exp(a - row[d])   op 1: out = a / (row[d] + 1e-16)   op 2: out = a * b   op 3: out = a * (b - row[d]).
+ * The host composes _softmax.py:82-88 as segment-max, op 0, segment-sum, op 1 (backward: op 2, segment-sum,
+ * op 3) with b200mp_segment_csr and its long-row plan, so no group is ever walked by a single lane group. */
+int b200mp_softmax_edge_op(int op, const float* a, const float* b, const float* row, const void* dst_of_edge,
+                           float* out, int64_t n_src, int64_t heads, int idx_dtype, void* stream);
+
+
+/* ------------------------------------------------------------------ multi-aggregation (one sweep, k outputs)
+ * Replaces FusedAggregation.forward (nn/aggr/fused.py:191-336: one scatter per base reduction plus the
+ * shared count) and the [sum, mean, min, max, var, std] members of MultiAggregation (nn/aggr/multi.py):
+ * every requested output of row i is derived from ONE walk over rowptr[i]:rowptr[i+1].
+ *   col != NULL: gather mode, row e reads x[col[e], :]  (x: [n_src, feat]);
+ *   col == NULL: segment mode, x is the destination-sorted message matrix [n_src = E, feat].
+ * out_* are nullable [n_rows, feat] tensors of val_dtype (NULL = not requested); ties_min / ties_max
+ * (nullable, fp32 [n_rows, feat]) receive the number of edges attaining the extremum, plus one where the
+ * extremum is 0 if count_self_zero (ATen's scatter_reduce backward rule) -- what the backward divides by.
+ * mean = sum / max(deg,1); var = sumsq / max(deg,1) - mean^2; std = sqrt(max(var,1e-5)), 0 where that is
+ * <= sqrt(1e-5) (fused.py:319-323); empty rows give 0 everywhere.  Hub rows: long-row plan of
+ * b200mp_csr_plan_* with partials of n_chunks * 6 * feat fp32. */
+int b200mp_multi_aggr_csr(const void* rowptr, const void* col, const void* x, void* out_sum, void* out_mean,
+                          void* out_min, void* out_max, void* out_var, void* out_std, float* ties_min,
+                          float* ties_max, int64_t n_rows, int64_t n_src, int64_t feat, int count_self_zero,
+                          const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
+                          int64_t n_chunks, int64_t chunk, float* partials, int idx_dtype, int val_dtype,
+                          void* stream);
+/* Backward of the above in one kernel.  The caller folds the output gradients into per-destination fp32
+ * rows (all nullable, [n_dst, feat]):  term_a (added), term_b (multiplies the message value),
+ * g_min = grad_min / ties_min with out_min (val_dtype), g_max / out_max likewise; then
+ *   grad(x_e) = sum over the destinations d of the value:  term_a[d] + x * term_b[d]
+ *               + [x == out_min[d]] * g_min[d] + [x == out_max[d]] * g_max[d].
+ * segment_mode != 0: n_items = E messages, idx = dst_of_edge [E] (ptr unused), x / grad_x: [E, feat];
+ * segment_mode == 0: n_items = n_src source rows, (ptr, idx) = transposed CSR (rowptr_t, col_t). */
+/* Elementwise prologue of the backward: folds the output gradients (nullable, [n_rows, feat] val_dtype) and
+ * the saved mean / std / tie counts into term_a, term_b, g_min / ties_min, g_max / ties_max (fp32).
+ * cnt = max(rowptr[i+1] - rowptr[i], 1); semi_grad drops the 2 x / cnt term of var / std (basic.py:106-110). */
+int b200mp_multi_aggr_prepare_backward(const void* rowptr, const void* g_sum, const void* g_mean,
+                                       const void* g_var, const void* g_std, const void* g_min,
+                                       const void* g_max, const void* mean, const void* std,
+                                       const float* ties_min, const float* ties_max, float* term_a,
+                                       float* term_b, float* gmin_out, float* gmax_out, int64_t n_rows,
+                                       int64_t feat, int semi_grad, int idx_dtype, int val_dtype, void* stream);
+int b200mp_multi_aggr_backward(const void* ptr, const void* idx, const void* x, const float* term_a,
+                               const float* term_b, const void* out_min, const float* g_min,
+                               const void* out_max, const float* g_max, void* grad_x, int64_t n_items,
+                               int64_t feat, int segment_mode, int idx_dtype, int val_dtype, void* stream);
 
 /* ------------------------------------------------------------------ fused GAT attention + aggregation
  * One sweep over the destination-sorted CSR per (node, head):

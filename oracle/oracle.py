@@ -263,3 +263,63 @@ def rgcn_conv(x, row, col, edge_type, weight, root, bias, reduce="mean"):
     lib().oracle_rgcn_conv(_p(x), _p(row), _p(col), _p(edge_type), _p(weight), _p(root), _p(bias),
                            _c(N), _c(row.size), _c(R), _c(Fin), _c(Fout), REDUCE[reduce], _p(out))
     return out
+
+
+FUSABLE = ("sum", "mean", "min", "max", "var", "std")
+
+
+def fused_aggregation(x, index, N, aggrs):
+    """torch_geometric/nn/aggr/fused.py:191-336 -- FusedAggregation.forward: one scatter per base reduction
+    (sum, x*x sum, min, max) plus the shared clamp(count, 1); mean (:243-256), var = pow_sum/count - mean*mean
+    (:258-283), std = sqrt(clamp(var, 1e-5)) with values <= sqrt(1e-5) set to 0 (:319-323).  fp32 throughout,
+    every intermediate rounded like the reference's separate ATen ops."""
+    x, index = _f(x), _i(index)
+    if x.shape[0] == 0:                      # test/nn/aggr/test_fused.py:46-55
+        return [np.zeros((N, x.shape[1]), np.float32) for _ in aggrs]
+    cnt = np.maximum(degree(index, N).astype(np.float32), np.float32(1)).reshape(-1, 1)
+    out = {}
+    s = scatter(x, index, N, "sum")
+    mean = (s / cnt).astype(np.float32)
+    if "var" in aggrs or "std" in aggrs:
+        pow_sum = scatter((x * x).astype(np.float32), index, N, "sum")
+        var = ((pow_sum / cnt).astype(np.float32) - (mean * mean).astype(np.float32)).astype(np.float32)
+        sd = np.sqrt(np.maximum(var, np.float32(1e-5))).astype(np.float32)
+        sd = np.where(sd <= np.float32(np.sqrt(1e-5)), np.float32(0), sd).astype(np.float32)
+        out["var"], out["std"] = var, sd
+    out["sum"], out["mean"] = s, mean
+    if "min" in aggrs:
+        out["min"] = scatter(x, index, N, "min")
+    if "max" in aggrs:
+        out["max"] = scatter(x, index, N, "max")
+    return [out[a] for a in aggrs]
+
+
+def fused_aggregation_backward(grads, x, index, N, aggrs, semi_grad=False):
+    """Gradient of fused_aggregation wrt x, term by term as autograd derives it from fused.py:
+    sum/mean -> gather (scatter_add_ backward), min/max -> ATen scatter_reduce rule
+    (oracle_scatter_backward), var -> 2 x g/cnt (dropped under semi_grad, basic.py:106-110) - 2 mean g/cnt,
+    std -> g / (2 std) where var >= 1e-5 survived the mask."""
+    x, index = _f(x), _i(index)
+    cnt = np.maximum(degree(index, N).astype(np.float64), 1.0).reshape(-1, 1)
+    outs = dict(zip(aggrs, fused_aggregation(x, index, N, aggrs)))
+    mean = scatter(x, index, N, "sum").astype(np.float64) / cnt
+    gx = np.zeros(x.shape, np.float64)
+    gvar = np.zeros((N, x.shape[1]), np.float64)
+    for a, g in zip(aggrs, grads):
+        g = _f(g).astype(np.float64)
+        if a == "sum":
+            gx += g[index]
+        elif a == "mean":
+            gx += (g / cnt)[index]
+        elif a in ("min", "max"):
+            gx += scatter_backward(g.astype(np.float32), x, outs[a], index, a).astype(np.float64)
+        elif a == "var":
+            gvar += g
+        elif a == "std":
+            sd = outs["std"].astype(np.float64)
+            gvar += np.where(sd > 0, g * 0.5 / np.where(sd > 0, sd, 1.0), 0.0)
+    if "var" in aggrs or "std" in aggrs:
+        gx += (-2.0 * gvar * mean / cnt)[index]
+        if not semi_grad:
+            gx += 2.0 * x.astype(np.float64) * (gvar / cnt)[index]
+    return gx.astype(np.float32)

@@ -64,7 +64,7 @@ __device__ __forceinline__ Vec16 ldg_row16(const void* p) {
 // Streaming 128-bit load (data read exactly once: evict first).
 __device__ __forceinline__ Vec16 ldg_stream16(const void* p) {
     Vec16 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
                  : "l"(p));
     return v;

@@ -1,0 +1,609 @@
+// multi_aggr.cu -- several aggregations of the same neighbourhood in ONE sweep over the edges.
+//
+// The reference's FusedAggregation (nn/aggr/fused.py:191-336) shares the degree count and the
+// sum between sum / mean / var / std, but still issues one scatter per base reduction (sum, x*x sum,
+// min, max), i.e. up to four passes over the [E, F] messages.  Here a lane group walks the CSR row
+// once and keeps six running values per feature in registers:
+//     s = sum x          q = sum x*x         mn, mx = min, max       cmn, cmx = #edges attaining them
+// and the epilogue derives every requested output:
+//     mean = s / max(deg,1)                       (fused.py:243-256)
+//     var  = q / max(deg,1) - mean*mean           (fused.py:258-283)
+//     std  = sqrt(max(var, 1e-5)), -> 0 where <= sqrt(1e-5)   (fused.py:319-323)
+//     min / max of an empty group = 0             (_scatter.py:98-100)
+//     ties_{min,max} = cm{n,x} (+1 if the result is 0: ATen's scatter_reduce backward counts the
+//                      zero-initialised `self`, see oracle_scatter_backward)
+// The additions are separate __fmul_rn / __fadd_rn in CSR order, so fp32 results are bit-identical
+// to the reference's CPU scatter_add_ for rows that are not chunked.
+//
+// Two addressing modes: GATHER (x is [n_cols, F], row e reads x[col[e]]) and segment mode
+// (col == nullptr: x is the materialised [E, F] message matrix, sorted by destination).
+// Hub rows use the same LongRowPlan as the SpMM; their partial state is six fp32 planes per chunk.
+//
+// Backward (both modes) is one kernel as well: with per-destination fp32 rows
+//     A  = g_sum + g_mean/cnt - 2 * g_var' * mean / cnt,   B = 2 * g_var' / cnt,
+//     Gmin = g_min / ties_min,  Gmax = g_max / ties_max          (g_var' = g_var + g_std / (2 std))
+// the gradient of one message value x is  A + x * B + [x == mn] * Gmin + [x == mx] * Gmax, summed over
+// the destinations the value was sent to (one in segment mode, the out-neighbours in gather mode).
+#include "csr_reduce.cuh"
+
+namespace b200mp {
+
+enum { MA_SUM = 0, MA_MEAN, MA_MIN, MA_MAX, MA_VAR, MA_STD, MA_TIES_MIN, MA_TIES_MAX, MA_SLOTS };
+
+struct MultiOut {
+    void* p[MA_SLOTS];      // [n_rows, feat]; slots 0..5 of the value dtype, the two tie planes fp32
+    int self_zero;          // count the zero-initialised self as a tie (scatter semantics)
+};
+
+// What the sweep has to carry per feature (compile-time: unused running values cost registers, and
+// the kernel's speed is set by how many warps fit on an SM).
+enum { MA_NEED_SUM = 1, MA_NEED_SQ = 2, MA_NEED_MM = 4, MA_NEED_TIES = 8 };
+constexpr int kModeSums = MA_NEED_SUM | MA_NEED_SQ;                                   // sum, mean, var, std
+constexpr int kModeMM = MA_NEED_MM;                                                   // min, max (inference)
+constexpr int kModeAll = MA_NEED_SUM | MA_NEED_SQ | MA_NEED_MM;                       // everything, inference
+constexpr int kModeAllTies = MA_NEED_SUM | MA_NEED_SQ | MA_NEED_MM | MA_NEED_TIES;    // training with min / max
+
+struct MultiState {
+    float s, q, mn, mx, cmn, cmx;
+};
+
+__device__ __forceinline__ void ms_init(MultiState& a) {
+    a.s = 0.f;
+    a.q = 0.f;
+    a.mn = __int_as_float(0x7f800000);
+    a.mx = __int_as_float(0xff800000);
+    a.cmn = 0.f;
+    a.cmx = 0.f;
+}
+template <int MODE>
+__device__ __forceinline__ void ms_push(MultiState& a, float v) {
+    if (MODE & MA_NEED_SUM) a.s = __fadd_rn(a.s, v);
+    if (MODE & MA_NEED_SQ) a.q = __fadd_rn(a.q, __fmul_rn(v, v));
+    if (MODE & MA_NEED_TIES) {
+        if (v < a.mn || v != v) { a.mn = v; a.cmn = 1.f; } else if (v == a.mn) a.cmn += 1.f;
+        if (v > a.mx || v != v) { a.mx = v; a.cmx = 1.f; } else if (v == a.mx) a.cmx += 1.f;
+    } else if (MODE & MA_NEED_MM) {
+        a.mn = (v < a.mn || v != v) ? v : a.mn;
+        a.mx = (v > a.mx || v != v) ? v : a.mx;
+    }
+}
+__device__ __forceinline__ void ms_merge(MultiState& a, const MultiState& b) {   // a then b, in edge order
+    a.s = __fadd_rn(a.s, b.s);
+    a.q = __fadd_rn(a.q, b.q);
+    if (b.mn < a.mn || b.mn != b.mn) { a.mn = b.mn; a.cmn = b.cmn; } else if (b.mn == a.mn) a.cmn += b.cmn;
+    if (b.mx > a.mx || b.mx != b.mx) { a.mx = b.mx; a.cmx = b.cmx; } else if (b.mx == a.mx) a.cmx += b.cmx;
+}
+
+// Epilogue for one (row, feature): derive the requested outputs from the running state.
+template <typename T>
+__device__ __forceinline__ void ms_store(const MultiOut& o, size_t idx, const MultiState& a, int64_t deg) {
+    const float cnt = static_cast<float>(deg < 1 ? 1 : deg);
+    const float mean = __fdiv_rn(a.s, cnt);
+    if (o.p[MA_SUM]) static_cast<T*>(o.p[MA_SUM])[idx] = ElemTraits<T>::from_float(a.s);
+    if (o.p[MA_MEAN]) static_cast<T*>(o.p[MA_MEAN])[idx] = ElemTraits<T>::from_float(mean);
+    const float mn = deg == 0 ? 0.f : a.mn, mx = deg == 0 ? 0.f : a.mx;
+    if (o.p[MA_MIN]) static_cast<T*>(o.p[MA_MIN])[idx] = ElemTraits<T>::from_float(mn);
+    if (o.p[MA_MAX]) static_cast<T*>(o.p[MA_MAX])[idx] = ElemTraits<T>::from_float(mx);
+    if (o.p[MA_TIES_MIN]) static_cast<float*>(o.p[MA_TIES_MIN])[idx] = a.cmn + ((o.self_zero && mn == 0.f) ? 1.f : 0.f);
+    if (o.p[MA_TIES_MAX]) static_cast<float*>(o.p[MA_TIES_MAX])[idx] = a.cmx + ((o.self_zero && mx == 0.f) ? 1.f : 0.f);
+    if (o.p[MA_VAR] || o.p[MA_STD]) {
+        const float var = __fsub_rn(__fdiv_rn(a.q, cnt), __fmul_rn(mean, mean));
+        if (o.p[MA_VAR]) static_cast<T*>(o.p[MA_VAR])[idx] = ElemTraits<T>::from_float(var);
+        if (o.p[MA_STD]) {
+            float sd = __fsqrt_rn(var < 1e-5f ? 1e-5f : var);
+            if (sd <= static_cast<float>(0.0031622776601683794)) sd = 0.f;   // math.sqrt(1e-5), fused.py:321
+            static_cast<T*>(o.p[MA_STD])[idx] = ElemTraits<T>::from_float(sd);
+        }
+    }
+}
+
+// Vector epilogue: the same, one 16-byte store per requested output.
+template <typename T>
+__device__ __forceinline__ void ms_store_vec(const MultiOut& o, size_t row, size_t row_bytes, size_t voff,
+                                             const MultiState (&a)[ElemTraits<T>::kPerVec], int64_t deg) {
+    constexpr int EPV = ElemTraits<T>::kPerVec;
+    const float cnt = static_cast<float>(deg < 1 ? 1 : deg);
+    float f[EPV], mean[EPV];
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) mean[i] = __fdiv_rn(a[i].s, cnt);
+    auto put = [&](int slot) {
+        stg_stream16(static_cast<char*>(o.p[slot]) + row * row_bytes + voff, ElemTraits<T>::pack(f));
+    };
+    if (o.p[MA_SUM]) {
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) f[i] = a[i].s;
+        put(MA_SUM);
+    }
+    if (o.p[MA_MEAN]) {
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) f[i] = mean[i];
+        put(MA_MEAN);
+    }
+    if (o.p[MA_MIN]) {
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) f[i] = deg == 0 ? 0.f : a[i].mn;
+        put(MA_MIN);
+    }
+    if (o.p[MA_MAX]) {
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) f[i] = deg == 0 ? 0.f : a[i].mx;
+        put(MA_MAX);
+    }
+    if (o.p[MA_VAR] || o.p[MA_STD]) {
+        float var[EPV];
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) var[i] = __fsub_rn(__fdiv_rn(a[i].q, cnt), __fmul_rn(mean[i], mean[i]));
+        if (o.p[MA_VAR]) {
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) f[i] = var[i];
+            put(MA_VAR);
+        }
+        if (o.p[MA_STD]) {
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) {
+                float sd = __fsqrt_rn(var[i] < 1e-5f ? 1e-5f : var[i]);
+                f[i] = sd <= static_cast<float>(0.0031622776601683794) ? 0.f : sd;
+            }
+            put(MA_STD);
+        }
+    }
+    // tie planes are fp32 whatever T is
+    const size_t e0 = row * (row_bytes / sizeof(T)) + voff / sizeof(T);
+    if (o.p[MA_TIES_MIN]) {
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) {
+            const float mn = deg == 0 ? 0.f : a[i].mn;
+            static_cast<float*>(o.p[MA_TIES_MIN])[e0 + i] = a[i].cmn + ((o.self_zero && mn == 0.f) ? 1.f : 0.f);
+        }
+    }
+    if (o.p[MA_TIES_MAX]) {
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) {
+            const float mx = deg == 0 ? 0.f : a[i].mx;
+            static_cast<float*>(o.p[MA_TIES_MAX])[e0 + i] = a[i].cmx + ((o.self_zero && mx == 0.f) ? 1.f : 0.f);
+        }
+    }
+}
+
+// Resident 128-thread CTAs per SM the register budget is capped for (occupancy is what hides the
+// gather latency: csr_reduce.cuh's sweep found 40 registers / 48 warps per SM best for the plain sum).
+constexpr int multi_minb(int mode, int epv) {
+    const int state = ((mode & MA_NEED_SUM) ? 1 : 0) + ((mode & MA_NEED_SQ) ? 1 : 0) + ((mode & MA_NEED_MM) ? 2 : 0) +
+                      ((mode & MA_NEED_TIES) ? 2 : 0);
+    const int regs = state * epv + 16 + 28;          // running values + 4 row vectors in flight + addressing / epilogue
+    return regs <= 40 ? 12 : regs <= 48 ? 10 : regs <= 64 ? 8 : regs <= 80 ? 6 : regs <= 96 ? 5 : 4;
+}
+
+// One lane group of G lanes per work item (row or hub chunk); a lane owns whole 16-byte vectors
+// (v = lig, lig + G, ...) and keeps 4 independent row loads in flight.
+template <typename T, typename I, int G, bool GATHER, int MODE>
+__global__ void __launch_bounds__(128, multi_minb(MODE, ElemTraits<T>::kPerVec))
+multi_aggr_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const T* __restrict__ x, MultiOut outs,
+                  int64_t n_rows, int n_vec, LongRowPlan plan) {
+    constexpr int EPV = ElemTraits<T>::kPerVec;
+    constexpr int UNR = 4;
+    const int lig = threadIdx.x & (G - 1);
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    int64_t row, begin, end;
+    bool is_chunk;
+    if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;
+    const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
+    const int64_t feat = static_cast<int64_t>(n_vec) * EPV;
+    const char* xb = reinterpret_cast<const char*>(x);
+    for (int v = lig; v < n_vec; v += G) {
+        MultiState a[EPV];
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) ms_init(a[i]);
+        const size_t voff = static_cast<size_t>(v) * 16;
+        for (int64_t e = begin; e < end; e += UNR) {
+            Vec16 buf[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (e + u < end) {
+                    const int64_t c = GATHER ? static_cast<int64_t>(ldg_idx(col + e + u)) : (e + u);
+                    buf[u] = GATHER ? ldg_row16(xb + static_cast<size_t>(c) * row_bytes + voff)
+                                    : ldg_stream16(xb + static_cast<size_t>(c) * row_bytes + voff);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (e + u < end) {
+                    float f[EPV];
+                    ElemTraits<T>::unpack(buf[u], f);
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) ms_push<MODE>(a[i], f[i]);
+                }
+            }
+        }
+        if (is_chunk) {
+            // partial state: [n_chunks][6][feat] fp32
+            float* pb = plan.partials + static_cast<size_t>(item) * 6 * feat + static_cast<size_t>(v) * EPV;
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) {
+                pb[i] = a[i].s;
+                pb[feat + i] = a[i].q;
+                pb[2 * feat + i] = a[i].mn;
+                pb[3 * feat + i] = a[i].mx;
+                pb[4 * feat + i] = a[i].cmn;
+                pb[5 * feat + i] = a[i].cmx;
+            }
+        } else {
+            ms_store_vec<T>(outs, static_cast<size_t>(row), row_bytes, voff, a, end - begin);
+        }
+    }
+}
+
+// Scalar variant for feature rows that are not whole aligned 16-byte vectors (F = 1 read-outs, odd widths).
+template <typename T, typename I, bool GATHER>
+__global__ void __launch_bounds__(128)
+multi_aggr_scalar_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const T* __restrict__ x,
+                         MultiOut outs, int64_t n_rows, int64_t feat, int g, LongRowPlan plan) {
+    const int lig = threadIdx.x & (g - 1);
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / g;
+    int64_t row, begin, end;
+    bool is_chunk;
+    if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;
+    for (int64_t f = lig; f < feat; f += g) {
+        MultiState a;
+        ms_init(a);
+        for (int64_t e = begin; e < end; e += 4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = 0.f;
+                if (e + u < end) {
+                    const int64_t c = GATHER ? static_cast<int64_t>(ldg_idx(col + e + u)) : (e + u);
+                    v[u] = ElemTraits<T>::to_float(x[c * feat + f]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e + u < end) ms_push<kModeAllTies>(a, v[u]);
+        }
+        if (is_chunk) {
+            float* pb = plan.partials + static_cast<size_t>(item) * 6 * feat + f;
+            pb[0] = a.s;
+            pb[feat] = a.q;
+            pb[2 * feat] = a.mn;
+            pb[3 * feat] = a.mx;
+            pb[4 * feat] = a.cmn;
+            pb[5 * feat] = a.cmx;
+        } else {
+            ms_store<T>(outs, static_cast<size_t>(row) * feat + f, a, end - begin);
+        }
+    }
+}
+
+// Fold the chunk states of every hub row in chunk (= edge) order.
+template <typename T, typename I>
+__global__ void __launch_bounds__(256)
+multi_aggr_combine_kernel(const I* __restrict__ rowptr, MultiOut outs, int64_t feat, LongRowPlan plan) {
+    const int64_t j = blockIdx.x;
+    if (j >= plan.n_long) return;
+    const int64_t row = plan.long_rows[j];
+    const int64_t c0 = plan.chunk_ptr[j], c1 = plan.chunk_ptr[j + 1];
+    const int64_t deg = static_cast<int64_t>(rowptr[row + 1]) - static_cast<int64_t>(rowptr[row]);
+    for (int64_t f = threadIdx.x; f < feat; f += blockDim.x) {
+        MultiState a;
+        ms_init(a);
+        for (int64_t c = c0; c < c1; ++c) {
+            const float* pb = plan.partials + static_cast<size_t>(c) * 6 * feat + f;
+            MultiState b{pb[0], pb[feat], pb[2 * feat], pb[3 * feat], pb[4 * feat], pb[5 * feat]};
+            ms_merge(a, b);
+        }
+        ms_store<T>(outs, static_cast<size_t>(row) * feat + f, a, deg);
+    }
+}
+
+// ---------------------------------------------------------------- backward
+struct MultiGrad {
+    const float* a;      // additive term              [n_dst, feat] or null
+    const float* b;      // multiplier of x            [n_dst, feat] or null
+    const void* mn;      // forward min (value dtype)  [n_dst, feat] or null
+    const float* gmin;   // g_min / ties_min
+    const void* mx;
+    const float* gmax;
+};
+
+template <typename T>
+__device__ __forceinline__ float mg_term(const MultiGrad& g, size_t di, float xv) {
+    float t = g.a ? __ldg(g.a + di) : 0.f;
+    if (g.b) t = fmaf(xv, __ldg(g.b + di), t);
+    if (g.mn && xv == ElemTraits<T>::to_float(static_cast<const T*>(g.mn)[di])) t += __ldg(g.gmin + di);
+    if (g.mx && xv == ElemTraits<T>::to_float(static_cast<const T*>(g.mx)[di])) t += __ldg(g.gmax + di);
+    return t;
+}
+
+// SEGMENT: item = message e, its single destination is dst_of_edge[e].
+// !SEGMENT: item = source row j; destinations are col_t[rowptr_t[j] : rowptr_t[j+1]].
+template <typename T, typename I, bool SEGMENT>
+__global__ void __launch_bounds__(256)
+multi_aggr_backward_kernel(const I* __restrict__ ptr, const I* __restrict__ idx, const T* __restrict__ x,
+                           MultiGrad g, T* __restrict__ grad_x, int64_t n_items, int64_t feat, int gw) {
+    const int lig = threadIdx.x & (gw - 1);
+    const int64_t j = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / gw;
+    if (j >= n_items) return;
+    if (SEGMENT) {
+        const size_t d = static_cast<size_t>(idx[j]) * feat;
+        for (int64_t f = lig; f < feat; f += gw) {
+            const float xv = ElemTraits<T>::to_float(x[j * feat + f]);
+            grad_x[j * feat + f] = ElemTraits<T>::from_float(mg_term<T>(g, d + f, xv));
+        }
+    } else {
+        const int64_t begin = ptr[j], end = ptr[j + 1];
+        for (int64_t f = lig; f < feat; f += gw) {
+            const float xv = ElemTraits<T>::to_float(x[j * feat + f]);
+            float acc = 0.f;
+            for (int64_t e = begin; e < end; ++e)
+                acc = __fadd_rn(acc, mg_term<T>(g, static_cast<size_t>(idx[e]) * feat + f, xv));
+            grad_x[j * feat + f] = ElemTraits<T>::from_float(acc);
+        }
+    }
+}
+
+// Folds the output gradients of one multi-aggregation call into the four per-destination fp32 rows the
+// backward sweep reads (one elementwise pass instead of ~15 separate tensor ops on [n_rows, feat]).
+struct MultiPrep {
+    const void *g_sum, *g_mean, *g_var, *g_std, *g_min, *g_max, *mean, *std;
+    const float *ties_min, *ties_max;
+    float *term_a, *term_b, *gmin, *gmax;
+};
+
+template <typename T, typename I>
+__global__ void __launch_bounds__(256)
+multi_aggr_prepare_kernel(const I* __restrict__ rowptr, MultiPrep p, int64_t n_rows, int64_t feat, bool semi_grad) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_rows * feat) return;
+    const int64_t row = i / feat;
+    const int64_t deg = static_cast<int64_t>(rowptr[row + 1]) - static_cast<int64_t>(rowptr[row]);
+    const float cnt = static_cast<float>(deg < 1 ? 1 : deg);
+    auto ld = [&](const void* q) { return ElemTraits<T>::to_float(static_cast<const T*>(q)[i]); };
+    if (p.term_a) {
+        float a = p.g_sum ? ld(p.g_sum) : 0.f;
+        if (p.g_mean) a += ld(p.g_mean) / cnt;
+        if (p.g_var || p.g_std) {
+            float gv = p.g_var ? ld(p.g_var) : 0.f;
+            if (p.g_std) {
+                // out = sqrt(clamp(var, 1e-5)) masked to 0 where <= sqrt(1e-5): gradient only where it survived
+                const float sd = ld(p.std);
+                if (sd > 0.f) gv += ld(p.g_std) * 0.5f / sd;
+            }
+            // var = E[x^2] - mean^2:  d/dx = 2 x / cnt (dropped under semi_grad, basic.py:106-110) - 2 mean / cnt
+            a -= 2.f * gv * ld(p.mean) / cnt;
+            if (p.term_b) p.term_b[i] = semi_grad ? 0.f : 2.f * gv / cnt;
+        }
+        p.term_a[i] = a;
+    }
+    if (p.gmin) p.gmin[i] = ld(p.g_min) / fmaxf(p.ties_min[i], 1.f);
+    if (p.gmax) p.gmax[i] = ld(p.g_max) / fmaxf(p.ties_max[i], 1.f);
+}
+
+template <typename T, typename I>
+int multi_prep_typed(const void* rowptr, MultiPrep p, int64_t n_rows, int64_t feat, int semi_grad, cudaStream_t stream) {
+    const int64_t n = n_rows * feat;
+    multi_aggr_prepare_kernel<T, I><<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(
+        static_cast<const I*>(rowptr), p, n_rows, feat, semi_grad != 0);
+    B200MP_LAUNCH_CHECK();
+    return B200MP_OK;
+}
+
+// fp32 vector form of the backward: a lane group per item, 16-byte loads of the (up to six)
+// per-destination rows, two destinations in flight.
+template <typename I, int G, bool SEGMENT>
+__global__ void __launch_bounds__(128, 6)
+multi_aggr_backward_vec_kernel(const I* __restrict__ ptr, const I* __restrict__ idx, const float* __restrict__ x,
+                               MultiGrad g, float* __restrict__ grad_x, int64_t n_items, int n_vec) {
+    constexpr int UNR = 2;
+    const int lig = threadIdx.x & (G - 1);
+    const int64_t j = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (j >= n_items) return;
+    const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
+    const int64_t begin = SEGMENT ? j : static_cast<int64_t>(ptr[j]);
+    const int64_t end = SEGMENT ? j + 1 : static_cast<int64_t>(ptr[j + 1]);
+    for (int v = lig; v < n_vec; v += G) {
+        const size_t voff = static_cast<size_t>(v) * 16;
+        float xv[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+        ElemTraits<float>::unpack(ldg_stream16(reinterpret_cast<const char*>(x) + static_cast<size_t>(j) * row_bytes + voff), xv);
+        for (int64_t e = begin; e < end; e += UNR) {
+            Vec16 b[UNR][6];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (e + u < end) {
+                    const size_t off = static_cast<size_t>(idx[e + u]) * row_bytes + voff;
+                    if (g.a) b[u][0] = ldg_row16(reinterpret_cast<const char*>(g.a) + off);
+                    if (g.b) b[u][1] = ldg_row16(reinterpret_cast<const char*>(g.b) + off);
+                    if (g.mn) {
+                        b[u][2] = ldg_row16(static_cast<const char*>(g.mn) + off);
+                        b[u][3] = ldg_row16(reinterpret_cast<const char*>(g.gmin) + off);
+                    }
+                    if (g.mx) {
+                        b[u][4] = ldg_row16(static_cast<const char*>(g.mx) + off);
+                        b[u][5] = ldg_row16(reinterpret_cast<const char*>(g.gmax) + off);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (e + u < end) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float t = g.a ? __uint_as_float(b[u][0].w[i]) : 0.f;
+                        if (g.b) t = fmaf(xv[i], __uint_as_float(b[u][1].w[i]), t);
+                        if (g.mn && xv[i] == __uint_as_float(b[u][2].w[i])) t += __uint_as_float(b[u][3].w[i]);
+                        if (g.mx && xv[i] == __uint_as_float(b[u][4].w[i])) t += __uint_as_float(b[u][5].w[i]);
+                        acc[i] = SEGMENT ? t : __fadd_rn(acc[i], t);
+                    }
+                }
+            }
+        }
+        stg_stream16(reinterpret_cast<char*>(grad_x) + static_cast<size_t>(j) * row_bytes + voff, ElemTraits<float>::pack(acc));
+    }
+}
+
+template <typename T, typename I, bool GATHER, int MODE>
+void multi_launch_mode(const I* rowptr, const I* col, const T* x, const MultiOut& outs, int64_t n_rows, int n_vec,
+                       const LongRowPlan& plan, cudaStream_t stream) {
+    const int64_t items = plan.n_chunks + n_rows;
+#define B200MP_MA(G_)                                                                                            \
+    multi_aggr_kernel<T, I, G_, GATHER, MODE><<<static_cast<unsigned>(ceil_div(items, 128 / G_)), 128, 0, stream>>>( \
+        rowptr, col, x, outs, n_rows, n_vec, plan)
+    if (n_vec <= 1) B200MP_MA(1);
+    else if (n_vec <= 2) B200MP_MA(2);
+    else if (n_vec <= 4) B200MP_MA(4);
+    else if (n_vec <= 8) B200MP_MA(8);
+    else if (n_vec <= 16) B200MP_MA(16);
+    else B200MP_MA(32);
+#undef B200MP_MA
+}
+
+template <typename T, typename I, bool GATHER>
+int multi_launch(const I* rowptr, const I* col, const T* x, MultiOut outs, int64_t n_rows, int64_t feat,
+                 LongRowPlan plan, cudaStream_t stream) {
+    const size_t row_bytes = static_cast<size_t>(feat) * sizeof(T);
+    const int64_t items = plan.n_chunks + n_rows;
+    bool vec_ok = row_bytes % 16 == 0 && aligned16(x);
+    for (int k = 0; k < MA_SLOTS; ++k) vec_ok = vec_ok && aligned16(outs.p[k]);
+    if (vec_ok) {
+        const int n_vec = static_cast<int>(row_bytes / 16);
+        const bool ties = outs.p[MA_TIES_MIN] || outs.p[MA_TIES_MAX];
+        const bool mm = ties || outs.p[MA_MIN] || outs.p[MA_MAX];
+        const bool sums = outs.p[MA_SUM] || outs.p[MA_MEAN] || outs.p[MA_VAR] || outs.p[MA_STD];
+        if (ties) multi_launch_mode<T, I, GATHER, kModeAllTies>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
+        else if (mm && sums) multi_launch_mode<T, I, GATHER, kModeAll>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
+        else if (mm) multi_launch_mode<T, I, GATHER, kModeMM>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
+        else multi_launch_mode<T, I, GATHER, kModeSums>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
+    } else {
+        int g = 1;
+        while (g < 32 && g < feat) g <<= 1;
+        multi_aggr_scalar_kernel<T, I, GATHER><<<static_cast<unsigned>(ceil_div(items, 128 / g)), 128, 0, stream>>>(
+            rowptr, col, x, outs, n_rows, feat, g, plan);
+    }
+    B200MP_LAUNCH_CHECK();
+    if (plan.n_long > 0) {
+        multi_aggr_combine_kernel<T, I><<<static_cast<unsigned>(plan.n_long), 256, 0, stream>>>(rowptr, outs, feat, plan);
+        B200MP_LAUNCH_CHECK();
+    }
+    return B200MP_OK;
+}
+
+template <typename T, typename I>
+int multi_typed(const void* rowptr, const void* col, const void* x, MultiOut outs, int64_t n_rows, int64_t feat,
+                LongRowPlan plan, cudaStream_t stream) {
+    if (col)
+        return multi_launch<T, I, true>(static_cast<const I*>(rowptr), static_cast<const I*>(col),
+                                        static_cast<const T*>(x), outs, n_rows, feat, plan, stream);
+    return multi_launch<T, I, false>(static_cast<const I*>(rowptr), static_cast<const I*>(nullptr),
+                                     static_cast<const T*>(x), outs, n_rows, feat, plan, stream);
+}
+
+template <typename I, bool SEGMENT>
+void multi_bwd_vec_launch(const I* ptr, const I* idx, const float* x, const MultiGrad& g, float* grad_x,
+                          int64_t n_items, int n_vec, cudaStream_t stream) {
+#define B200MP_MB(G_)                                                                                        \
+    multi_aggr_backward_vec_kernel<I, G_, SEGMENT><<<static_cast<unsigned>(ceil_div(n_items, 128 / G_)), 128, 0, stream>>>( \
+        ptr, idx, x, g, grad_x, n_items, n_vec)
+    if (n_vec <= 1) B200MP_MB(1);
+    else if (n_vec <= 2) B200MP_MB(2);
+    else if (n_vec <= 4) B200MP_MB(4);
+    else if (n_vec <= 8) B200MP_MB(8);
+    else if (n_vec <= 16) B200MP_MB(16);
+    else B200MP_MB(32);
+#undef B200MP_MB
+}
+
+template <typename T, typename I>
+int multi_bwd_typed(const void* ptr, const void* idx, const void* x, MultiGrad g, void* grad_x, int64_t n_items,
+                    int64_t feat, int segment, cudaStream_t stream) {
+    const bool vec_ok = sizeof(T) == 4 && feat % 4 == 0 && aligned16(x) && aligned16(grad_x) && aligned16(g.a) &&
+                        aligned16(g.b) && aligned16(g.mn) && aligned16(g.gmin) && aligned16(g.mx) && aligned16(g.gmax);
+    if (vec_ok) {
+        const int n_vec = static_cast<int>(feat / 4);
+        if (segment)
+            multi_bwd_vec_launch<I, true>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
+                                          static_cast<const float*>(x), g, static_cast<float*>(grad_x), n_items, n_vec, stream);
+        else
+            multi_bwd_vec_launch<I, false>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
+                                           static_cast<const float*>(x), g, static_cast<float*>(grad_x), n_items, n_vec, stream);
+        B200MP_LAUNCH_CHECK();
+        return B200MP_OK;
+    }
+    int gw = 1;
+    while (gw < 32 && gw < feat) gw <<= 1;
+    const unsigned blocks = static_cast<unsigned>(ceil_div(n_items, 256 / gw));
+    if (segment)
+        multi_aggr_backward_kernel<T, I, true><<<blocks, 256, 0, stream>>>(
+            static_cast<const I*>(ptr), static_cast<const I*>(idx), static_cast<const T*>(x), g,
+            static_cast<T*>(grad_x), n_items, feat, gw);
+    else
+        multi_aggr_backward_kernel<T, I, false><<<blocks, 256, 0, stream>>>(
+            static_cast<const I*>(ptr), static_cast<const I*>(idx), static_cast<const T*>(x), g,
+            static_cast<T*>(grad_x), n_items, feat, gw);
+    B200MP_LAUNCH_CHECK();
+    return B200MP_OK;
+}
+
+}  // namespace b200mp
+
+using namespace b200mp;
+
+#define DISPATCH_T_I(FN, ...)                                                        \
+    do {                                                                             \
+        if (val_dtype == B200MP_F32 && idx_dtype == B200MP_I32) return FN<float, int32_t>(__VA_ARGS__);        \
+        if (val_dtype == B200MP_F32 && idx_dtype == B200MP_I64) return FN<float, int64_t>(__VA_ARGS__);        \
+        if (val_dtype == B200MP_BF16 && idx_dtype == B200MP_I32) return FN<__nv_bfloat16, int32_t>(__VA_ARGS__); \
+        if (val_dtype == B200MP_BF16 && idx_dtype == B200MP_I64) return FN<__nv_bfloat16, int64_t>(__VA_ARGS__); \
+        set_error("unsupported dtype combination val=%d idx=%d", val_dtype, idx_dtype);                         \
+        return B200MP_ERR_UNSUPPORTED;                                                                          \
+    } while (0)
+
+extern "C" int b200mp_multi_aggr_csr(const void* rowptr, const void* col, const void* x, void* out_sum,
+                                     void* out_mean, void* out_min, void* out_max, void* out_var, void* out_std,
+                                     float* ties_min, float* ties_max, int64_t n_rows, int64_t n_src,
+                                     int64_t feat, int count_self_zero, const int64_t* long_rows,
+                                     const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks,
+                                     int64_t chunk, float* partials, int idx_dtype, int val_dtype, void* stream) {
+    B200MP_CHECK_ARG(n_rows >= 0 && n_src >= 0 && feat >= 0);
+    if (n_rows == 0 || feat == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(rowptr && (x || n_src == 0));
+    B200MP_CHECK_ARG(n_long_rows >= 0 && n_chunks >= 0);
+    B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && partials && chunk > 0));
+    MultiOut outs{{out_sum, out_mean, out_min, out_max, out_var, out_std, ties_min, ties_max}, count_self_zero != 0};
+    LongRowPlan plan{long_rows, chunk_ptr, n_long_rows, n_long_rows ? n_chunks : 0, chunk, partials,
+                     nullptr, 0, 0, nullptr, 0};
+    DISPATCH_T_I(multi_typed, rowptr, col, x, outs, n_rows, feat, plan, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200mp_multi_aggr_backward(const void* ptr, const void* idx, const void* x, const float* term_a,
+                                          const float* term_b, const void* out_min, const float* g_min,
+                                          const void* out_max, const float* g_max, void* grad_x,
+                                          int64_t n_items, int64_t feat, int segment_mode, int idx_dtype,
+                                          int val_dtype, void* stream) {
+    B200MP_CHECK_ARG(n_items >= 0 && feat >= 0);
+    if (n_items == 0 || feat == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(idx && x && grad_x && (segment_mode || ptr));
+    B200MP_CHECK_ARG((!out_min || g_min) && (!out_max || g_max));
+    MultiGrad g{term_a, term_b, out_min, g_min, out_max, g_max};
+    DISPATCH_T_I(multi_bwd_typed, ptr, idx, x, g, grad_x, n_items, feat, segment_mode,
+                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200mp_multi_aggr_prepare_backward(const void* rowptr, const void* g_sum, const void* g_mean,
+                                                  const void* g_var, const void* g_std, const void* g_min,
+                                                  const void* g_max, const void* mean, const void* std,
+                                                  const float* ties_min, const float* ties_max, float* term_a,
+                                                  float* term_b, float* gmin_out, float* gmax_out, int64_t n_rows,
+                                                  int64_t feat, int semi_grad, int idx_dtype, int val_dtype,
+                                                  void* stream) {
+    B200MP_CHECK_ARG(n_rows >= 0 && feat >= 0);
+    if (n_rows == 0 || feat == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(rowptr);
+    B200MP_CHECK_ARG(!(g_sum || g_mean || g_var || g_std) || term_a);
+    B200MP_CHECK_ARG(!(g_var || g_std) || (mean && term_b));
+    B200MP_CHECK_ARG(!g_std || std);
+    B200MP_CHECK_ARG(!gmin_out || (g_min && ties_min));
+    B200MP_CHECK_ARG(!gmax_out || (g_max && ties_max));
+    MultiPrep p{g_sum, g_mean, g_var, g_std, g_min, g_max, mean, std, ties_min, ties_max,
+                (g_sum || g_mean || g_var || g_std) ? term_a : nullptr, (g_var || g_std) ? term_b : nullptr,
+                gmin_out, gmax_out};
+    DISPATCH_T_I(multi_prep_typed, rowptr, p, n_rows, feat, semi_grad, static_cast<cudaStream_t>(stream));
+}

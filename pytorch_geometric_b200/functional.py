@@ -85,7 +85,8 @@ def aggregate(graph: CSRGraph, x: Tensor, reduce: str = "sum", edge_weight: Opti
 class _Segment(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src: Tensor, ptr: Tensor, reduce: str):
-        out = ops.segment_csr(src, ptr, reduce)
+        ctx.plan = ops.segment_plan(ptr, src.size(0))      # hub segments are cut into chunks (csr_reduce.cuh)
+        out = ops.segment_csr(src, ptr, reduce, ctx.plan)
         ctx.reduce = reduce
         ctx.save_for_backward(ptr, src if reduce in ("min", "max") else None, out if reduce in ("min", "max") else None)
         return out
@@ -106,7 +107,7 @@ class _Segment(torch.autograd.Function):
             # _segment_reduce backward: even split among ties (no zero-initialised self here)
             s2, o2 = src.view(src.size(0), -1), out.view(out.size(0), -1)
             eq = (s2 == ops.gather_rows(o2, index)).to(s2.dtype)
-            ties = ops.segment_csr(eq, ptr, "sum")
+            ties = ops.segment_csr(eq, ptr, "sum", ctx.plan)
             g = eq * ops.gather_rows(g2 / ties.clamp(min=1), index)
         return g.view((n_src, ) + tuple(grad_out.shape[1:])), None, None
 
@@ -151,19 +152,22 @@ def scatter_coo(src: Tensor, index: Tensor, dim_size: int, reduce: str = "sum") 
 
 class _SoftmaxCSR(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, src: Tensor, ptr: Tensor):
-        out = ops.softmax_csr(src, ptr)
-        ctx.save_for_backward(out, ptr)
+    def forward(ctx, src: Tensor, ptr: Tensor, index: Optional[Tensor]):
+        ctx.plan = ops.segment_plan(ptr, src.size(0))        # hub groups: chunked path (ops.softmax_csr)
+        if ctx.plan is not None and index is None:
+            index = ops.ptr2index(ptr, src.size(0))
+        out = ops.softmax_csr(src, ptr, ctx.plan, index)
+        ctx.save_for_backward(out, ptr, index)
         return out
 
     @staticmethod
     def backward(ctx, grad_out: Tensor):
-        out, ptr = ctx.saved_tensors
-        return ops.softmax_csr_backward(out, grad_out, ptr), None
+        out, ptr, index = ctx.saved_tensors
+        return ops.softmax_csr_backward(out, grad_out, ptr, ctx.plan, index), None, None
 
 
-def softmax_csr(src: Tensor, ptr: Tensor) -> Tensor:
-    return _SoftmaxCSR.apply(src, ptr)
+def softmax_csr(src: Tensor, ptr: Tensor, index: Optional[Tensor] = None) -> Tensor:
+    return _SoftmaxCSR.apply(src, ptr, index)
 
 
 class _GATFused(torch.autograd.Function):
@@ -200,3 +204,58 @@ def gat_attention(graph: CSRGraph, xh: Tensor, a_src: Tensor, a_dst: Tensor, hea
     xh: [num_src, H*C]; returns out [num_dst, H*C] (and alpha [E, H] in CSR order)."""
     out, alpha = _GATFused.apply(xh, a_src, a_dst, graph, heads, chan, float(negative_slope), return_alpha)
     return (out, alpha) if return_alpha else out
+
+
+class _MultiAggregate(torch.autograd.Function):
+    """k aggregations of one neighbourhood in one sweep (FusedAggregation, nn/aggr/fused.py:191-336).
+    `where` is a CSRGraph (gather mode: x is [num_src, F]) or a (ptr, index) pair (segment mode: x is the
+    destination-sorted [E, F] message matrix)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, where, names: tuple, semi_grad: bool, count_self_zero: bool):
+        gather = isinstance(where, CSRGraph)
+        if gather:
+            rowptr, col, n_rows, plan = where.rowptr, where.col, where.num_dst, where.plan
+        else:
+            rowptr, col, n_rows, plan = where[0], None, where[0].numel() - 1, where[2]
+        need_grad = x.requires_grad
+        # the var / std gradients need the group mean even when it is not an output
+        extra = ("mean", ) if need_grad and "mean" not in names and ("var" in names or "std" in names) else ()
+        res = ops.multi_aggr_csr(rowptr, col, x, n_rows, tuple(names) + extra, plan, with_ties=need_grad,
+                                 count_self_zero=count_self_zero)
+        ctx.where, ctx.names, ctx.gather, ctx.semi_grad = where, tuple(names), gather, semi_grad
+        ctx.save_for_backward(x, res.get("min"), res.get("max"), res.get("ties_min"), res.get("ties_max"),
+                              res.get("mean"), res.get("std"))
+        return tuple(res[n] for n in names)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, omin, omax, tmin, tmax, mean, std = ctx.saved_tensors
+        where = ctx.where
+        g = {n: (None if gr is None else gr.to(x.dtype)) for n, gr in zip(ctx.names, grads)}
+        if all(v is None for v in g.values()):
+            return None, None, None, None, None
+        rowptr = where.rowptr if ctx.gather else where[0]
+        term_a, term_b, gmin, gmax = ops.multi_aggr_prepare_backward(rowptr, g, mean, std, tmin, tmax, ctx.semi_grad)
+        omin = omin if gmin is not None else None
+        omax = omax if gmax is not None else None
+        if ctx.gather:
+            where.build_transpose()
+            gx = ops.multi_aggr_backward(where.rowptr_t, where.col_t, x, term_a, term_b, omin, gmin, omax, gmax, False)
+        else:
+            gx = ops.multi_aggr_backward(None, where[1], x, term_a, term_b, omin, gmin, omax, gmax, True)
+        return gx, None, None, None, None
+
+
+def multi_aggregate(where, x: Tensor, aggrs, semi_grad: bool = False, count_self_zero: bool = True):
+    """[aggr(x) for aggr in aggrs] with aggrs from {sum, mean, min, max, var, std}, one sweep over the edges.
+    where: CSRGraph (x: [num_src, F]) or (ptr, index[, plan]) for a destination-sorted [E, F] message matrix."""
+    names = tuple({"add": "sum"}.get(a, a) for a in aggrs)
+    if len(set(names)) != len(names):
+        raise ValueError("duplicate aggregation in the fused list")
+    for n in names:
+        if n not in ops.MULTI_AGGRS:
+            raise ValueError(f"cannot fuse aggregation '{n}' (supported: {ops.MULTI_AGGRS})")
+    if not isinstance(where, CSRGraph):
+        where = tuple(where) + (None, ) * (3 - len(where))
+    return list(_MultiAggregate.apply(x, where, names, semi_grad, count_self_zero))

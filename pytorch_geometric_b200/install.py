@@ -6,6 +6,8 @@ INTEGRATION.md).  The reference dispatches at call time on Python-level seams
   torch_geometric.utils._segment.segment      -> utils.segment
   torch_geometric.utils._softmax.softmax      -> utils.softmax
   torch_geometric.utils._spmm.spmm            -> utils.spmm  (CSRGraph / torch.sparse_csr on CUDA)
+  torch_geometric.nn.aggr.fused.FusedAggregation.forward -> the one-sweep multi-aggregation
+        (so MultiAggregation / PNA-style `aggr=[...]` lists on CUDA tensors take one pass over the messages)
   torch_geometric.nn.{GCNConv,SAGEConv,GINConv,GATConv,RGCNConv} -> the fused layers (optional)
 
 plus every module that imported those names (`from torch_geometric.utils import scatter` binds
@@ -87,6 +89,27 @@ def install(layers: bool = False) -> Dict[str, int]:
             setattr(mod, "spmm", spmm)
             n += 1
     counts["spmm"] = n
+
+    # FusedAggregation.forward (nn/aggr/fused.py:191): every fusable list except those containing 'mul'
+    from torch_geometric.nn.aggr.fused import FusedAggregation as TheirFused
+
+    from .nn import aggr as our_aggr
+    theirs_fwd = TheirFused.forward
+
+    def fused_forward(self, x, index=None, ptr=None, dim_size=None, dim=-2):
+        names = [our_aggr.FusedAggregation.NAME.get(n) for n in self.aggr_names]
+        if not getattr(x, "is_cuda", False) or None in names or x.dim() != 2 or index is None:
+            return theirs_fwd(self, x, index, ptr, dim_size, dim)
+        if dim_size is None:
+            dim_size = ptr.numel() - 1 if ptr is not None else (int(index.max()) + 1 if index.numel() > 0 else 0)
+        uniq = list(dict.fromkeys(names))
+        # the reference ignores `ptr` here and scatters by `index`; a given ptr means the index is sorted
+        outs = dict(zip(uniq, our_aggr._fused_forward(uniq, self.semi_grad, x, index, ptr, dim_size, dim, False)))
+        return [outs[n] for n in names]
+
+    _PATCHED.append((TheirFused, "forward", theirs_fwd))
+    TheirFused.forward = fused_forward
+    counts["fused_aggregation"] = 1
 
     if layers:
         import torch_geometric.nn as tgnn

@@ -282,14 +282,27 @@ def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_ro
     return out
 
 
-def segment_csr(src: Tensor, ptr: Tensor, reduce: str = "sum") -> Tensor:
+SEGMENT_PLAN_MIN_ROWS = 1 << 16   # below this many source rows a hub segment cannot matter: skip the plan (and its sync)
+SEGMENT_CHUNK = 512               # rows per chunk of a long segment (same as graph.DEFAULT_CHUNK)
+
+
+def segment_plan(ptr: Tensor, n_src: int) -> Optional["LongRowPlan"]:
+    """Long-segment plan for segment_csr / multi_aggr_csr (None when the input is too small to need one)."""
+    if n_src < SEGMENT_PLAN_MIN_ROWS:
+        return None
+    plan = LongRowPlan(ptr, SEGMENT_CHUNK)
+    return plan if plan.n_long else None
+
+
+def segment_csr(src: Tensor, ptr: Tensor, reduce: str = "sum", plan: Optional["LongRowPlan"] = None) -> Tensor:
     _cuda(src, ptr)
     src = src.contiguous()
     n_rows = ptr.numel() - 1
     flat = src.view(src.size(0), -1)
     out = torch.empty((n_rows, flat.size(1)), dtype=src.dtype, device=src.device)
-    check(lib().b200mp_segment_csr(_p(ptr), _p(flat), _p(out), n_rows, flat.size(0), flat.size(1), REDUCE[reduce],
-                                   _idt(ptr), _vdt(src), _stream()), "segment_csr")
+    pargs, _ = _plan_args(plan, flat.size(1), src.device)
+    _timed("segment_csr", 2 if pargs[2] else 1, lib().b200mp_segment_csr, _p(ptr), _p(flat), _p(out), n_rows,
+           flat.size(0), flat.size(1), REDUCE[reduce], *pargs, _idt(ptr), _vdt(src), _stream())
     return out.view((n_rows, ) + tuple(src.shape[1:]))
 
 
@@ -360,23 +373,48 @@ def gather_rows(x: Tensor, index: Tensor, scale: Optional[Tensor] = None) -> Ten
     return out.view((index.numel(), ) + tuple(x.shape[1:]))
 
 
-def softmax_csr(src: Tensor, ptr: Tensor) -> Tensor:
+def _softmax_edge_op(op: int, a: Tensor, b: Optional[Tensor], row: Optional[Tensor], dst: Optional[Tensor]) -> Tensor:
+    out = torch.empty_like(a)
+    _timed("softmax_edge_op", 1, lib().b200mp_softmax_edge_op, op, _p(a), _p(b), _p(row), _p(dst), _p(out), a.size(0),
+           a.size(1), _idt(dst) if dst is not None else I64, _stream())
+    return out
+
+
+def softmax_csr(src: Tensor, ptr: Tensor, plan: Optional["LongRowPlan"] = None,
+                index: Optional[Tensor] = None) -> Tensor:
+    """Per-group softmax over ptr ranges.  With a long-row plan (hub groups) the reference's own sequence
+    -- segment max, exp(x - max), segment sum, divide (_softmax.py:82-88) -- runs on the chunked segmented
+    reduce and edge-parallel kernels; otherwise one fused three-pass kernel per group."""
     _cuda(src, ptr)
     src = src.contiguous().float()
     flat = src.view(src.size(0), -1)
+    if plan is not None and plan.n_long:
+        if index is None:
+            index = ptr2index(ptr, flat.size(0))
+        mx = segment_csr(flat, ptr, "max", plan)
+        ex = _softmax_edge_op(0, flat, None, mx, index)
+        den = segment_csr(ex, ptr, "sum", plan)
+        return _softmax_edge_op(1, ex, None, den, index).view(src.shape)
     out = torch.empty_like(flat)
-    check(lib().b200mp_softmax_csr(_p(ptr), _p(flat), _p(out), ptr.numel() - 1, flat.size(0), flat.size(1),
-                                   _idt(ptr), _stream()), "softmax_csr")
+    _timed("softmax_csr", 1, lib().b200mp_softmax_csr, _p(ptr), _p(flat), _p(out), ptr.numel() - 1, flat.size(0),
+           flat.size(1), _idt(ptr), _stream())
     return out.view(src.shape)
 
 
-def softmax_csr_backward(out: Tensor, grad_out: Tensor, ptr: Tensor) -> Tensor:
+def softmax_csr_backward(out: Tensor, grad_out: Tensor, ptr: Tensor, plan: Optional["LongRowPlan"] = None,
+                         index: Optional[Tensor] = None) -> Tensor:
     _cuda(out, grad_out, ptr)
     out, grad_out = out.contiguous(), grad_out.contiguous().float()
     flat = out.view(out.size(0), -1)
+    gflat = grad_out.view(flat.shape)
+    if plan is not None and plan.n_long:
+        if index is None:
+            index = ptr2index(ptr, flat.size(0))
+        dot = segment_csr(_softmax_edge_op(2, flat, gflat, None, None), ptr, "sum", plan)
+        return _softmax_edge_op(3, flat, gflat, dot, index).view(out.shape)
     g = torch.empty_like(flat)
-    check(lib().b200mp_softmax_csr_backward(_p(ptr), _p(flat), _p(grad_out), _p(g), ptr.numel() - 1, flat.size(0),
-                                            flat.size(1), _idt(ptr), _stream()), "softmax_csr_backward")
+    _timed("softmax_csr_backward", 1, lib().b200mp_softmax_csr_backward, _p(ptr), _p(flat), _p(gflat), _p(g),
+           ptr.numel() - 1, flat.size(0), flat.size(1), _idt(ptr), _stream())
     return g.view(out.shape)
 
 
@@ -429,6 +467,83 @@ def gat_fused_csr_backward(rowptr, col, dst_of_edge, rowptr_t, col_t, t2csr, xh,
            _p(grad_out), _p(grad_pre), _p(rowdot), _p(gxh), _p(gas), _p(gad), n_rows, n_src, col.numel(), heads, chan,
            float(slope), *pargs, it, _vdt(xh), _stream())
     return gxh, gas, gad
+
+
+MULTI_AGGRS = ("sum", "mean", "min", "max", "var", "std")
+
+
+def multi_aggr_csr(rowptr: Tensor, col: Optional[Tensor], x: Tensor, n_rows: int, want, plan=None,
+                   with_ties: bool = False, count_self_zero: bool = True) -> dict:
+    """Every aggregation named in `want` (subset of MULTI_AGGRS) from one sweep over the CSR rows.
+    col=None: segment mode (x is the destination-sorted [E, F] message matrix).  Returns a dict
+    name -> [n_rows, F]; with_ties adds fp32 'ties_min' / 'ties_max' when min / max are wanted."""
+    _cuda(rowptr, col, x)
+    if x.dim() != 2:
+        raise ValueError("multi_aggr_csr expects a 2-D feature matrix")
+    x = x.contiguous()
+    it = _same_idx(rowptr, col) if col is not None else _idt(rowptr)
+    F = x.size(1)
+    res = {}
+    for name in want:
+        if name not in MULTI_AGGRS:
+            raise ValueError(f"cannot fuse aggregation '{name}' (supported: {MULTI_AGGRS})")
+        res[name] = torch.empty(n_rows, F, dtype=x.dtype, device=x.device)
+    if with_ties:
+        for name in ("min", "max"):
+            if name in res:
+                res["ties_" + name] = torch.empty(n_rows, F, dtype=torch.float32, device=x.device)
+    pargs, _ = _plan_args(plan, 6 * F, x.device)
+    _timed("multi_aggr_csr", 2 if pargs[2] else 1, lib().b200mp_multi_aggr_csr, _p(rowptr), _p(col), _p(x),
+           *[_p(res.get(n)) for n in MULTI_AGGRS], _p(res.get("ties_min")), _p(res.get("ties_max")), n_rows,
+           x.size(0), F, int(bool(count_self_zero)), *pargs, it, _vdt(x), _stream())
+    return res
+
+
+def multi_aggr_prepare_backward(rowptr: Tensor, grads: dict, mean: Optional[Tensor], std: Optional[Tensor],
+                                ties_min: Optional[Tensor], ties_max: Optional[Tensor], semi_grad: bool):
+    """(term_a, term_b, g_min / ties_min, g_max / ties_max) for multi_aggr_backward from the output
+    gradients `grads` (name -> [n_rows, F] or None), in one elementwise kernel."""
+    ref = next(g for g in grads.values() if g is not None)
+    n_rows, F = ref.shape
+    g = {k: (None if v is None else v.contiguous()) for k, v in grads.items()}
+    _cuda(rowptr, *g.values(), mean, std, ties_min, ties_max)
+
+    def new():
+        return torch.empty(n_rows, F, dtype=torch.float32, device=ref.device)
+
+    need_a = any(g.get(k) is not None for k in ("sum", "mean", "var", "std"))
+    need_b = any(g.get(k) is not None for k in ("var", "std"))
+    term_a = new() if need_a else None
+    term_b = new() if need_b else None
+    gmin = new() if g.get("min") is not None else None
+    gmax = new() if g.get("max") is not None else None
+    _timed("multi_aggr_prepare_backward", 1, lib().b200mp_multi_aggr_prepare_backward, _p(rowptr), _p(g.get("sum")),
+           _p(g.get("mean")), _p(g.get("var")), _p(g.get("std")), _p(g.get("min")), _p(g.get("max")), _p(mean),
+           _p(std), _p(ties_min), _p(ties_max), _p(term_a), _p(term_b), _p(gmin), _p(gmax), n_rows, F,
+           int(bool(semi_grad)), _idt(rowptr), _vdt(ref), _stream())
+    return term_a, (None if semi_grad else term_b), gmin, gmax
+
+
+def multi_aggr_backward(ptr: Optional[Tensor], idx: Tensor, x: Tensor, term_a: Optional[Tensor],
+                        term_b: Optional[Tensor], out_min: Optional[Tensor], g_min: Optional[Tensor],
+                        out_max: Optional[Tensor], g_max: Optional[Tensor], segment_mode: bool) -> Tensor:
+    """grad wrt the message values (see b200mp_multi_aggr_backward).  segment_mode: idx = destination of
+    every message; otherwise (ptr, idx) is the transposed CSR and x the [n_src, F] source matrix."""
+    _cuda(ptr, idx, x, term_a, term_b, out_min, g_min, out_max, g_max)
+    x = x.contiguous()
+
+    def f32(t):
+        return None if t is None else t.contiguous().float()
+
+    term_a, term_b, g_min, g_max = f32(term_a), f32(term_b), f32(g_min), f32(g_max)
+    out_min = None if out_min is None else out_min.contiguous()
+    out_max = None if out_max is None else out_max.contiguous()
+    gx = torch.empty_like(x)
+    it = _idt(idx) if segment_mode else _same_idx(ptr, idx)
+    _timed("multi_aggr_backward", 1, lib().b200mp_multi_aggr_backward, _p(ptr), _p(idx), _p(x), _p(term_a),
+           _p(term_b), _p(out_min), _p(g_min), _p(out_max), _p(g_max), _p(gx), x.size(0), x.size(1),
+           int(bool(segment_mode)), it, _vdt(x), _stream())
+    return gx
 
 
 def device_info() -> dict:

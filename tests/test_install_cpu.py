@@ -61,3 +61,25 @@ def test_install_layers_swaps_conv_classes(tg):
     finally:
         b200.uninstall()
     assert tg.nn.GCNConv is orig
+
+
+def test_install_routes_fused_aggregation_and_cpu_falls_through(tg):
+    from torch_geometric.nn.aggr.fused import FusedAggregation
+
+    import pytorch_geometric_b200.install as b200
+
+    orig = FusedAggregation.forward
+    aggr = FusedAggregation(["sum", "mean", "max", "std"])
+    x = torch.randn(12, 3)
+    index = torch.tensor([0, 0, 1, 1, 1, 3, 3, 3, 3, 4, 4, 0])
+    before = aggr(x, index, dim_size=6)
+    counts = b200.install()
+    try:
+        assert counts["fused_aggregation"] == 1 and FusedAggregation.forward is not orig
+        after = aggr(x, index, dim_size=6)             # CPU tensors: untouched reference
+        assert all(torch.equal(a, b) for a, b in zip(before, after))
+        # a list with 'mul' is not fusable by the engine and must fall through as well
+        assert len(FusedAggregation(["sum", "mul"])(x, index, dim_size=6)) == 2
+    finally:
+        b200.uninstall()
+    assert FusedAggregation.forward is orig
