@@ -236,6 +236,8 @@ def run_b200(args):
         ops.set_option("gemm_mode", args.gemm_mode)
     if args.gemm_prefetch >= 0:
         ops.set_option("gemm_prefetch", args.gemm_prefetch)
+    if args.gemm_bsplit >= 0:
+        dense.set_b_split(bool(args.gemm_bsplit))
     torch.manual_seed(1234 + rank)
     conv = GCNConv(F, F, cached=True).to(dev)
     with torch.no_grad():
@@ -462,6 +464,8 @@ def main():
     ap.add_argument("--gemm-bk", type=int, default=0, help="k-block width of the tcgen05 GEMM (16 or 32; 0 = library default)")
     ap.add_argument("--gemm-prefetch", type=int, default=-1, help="TMA L2-prefetch distance of the GEMM in k-blocks")
     ap.add_argument("--gemm-mode", type=int, default=-1, help="0 = SS-mode GEMM, 1 = TS-mode (A in TMEM); -1 = library default")
+    ap.add_argument("--gemm-bsplit", type=int, default=-1,
+                    help="1 = the GEMM kernel splits W tiles itself (one L2 read of W per tile), 0 = pre-split W_hi / W_lo")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,

@@ -300,7 +300,9 @@ int b200mp_gat_fused_csr_backward(const void* rowptr, const void* col, const voi
  *   b200mp_linear_tf32x3            y [M,N]  = x [M,K] . w[N,K]^T
  *   b200mp_linear_grad_input_tf32x3 gx[M,K]  = g [M,N] . w[N,K]
  *   b200mp_linear_grad_weight_tf32x3 gw[N,K] = g [M,N]^T . x[M,K]   (deterministic split-K)
- * w_hi/w_lo come from b200mp_split_tf32 (w = w_hi + w_lo, w_hi = rn_tf32(w)).  All matrices
+ * w_hi/w_lo come from b200mp_split_tf32 (w = w_hi + w_lo, w_hi = rn_tf32(w)); w_lo == NULL means w_hi is
+ * the UNSPLIT weight and the kernel splits each B tile in shared memory (one L2 read of W per tile instead
+ * of two; needs an output width that is a multiple of 128).  All matrices
  * row-major, contiguous, 16-byte aligned.  Shape limits (else B200MP_ERR_UNSUPPORTED and the caller
  * uses a library GEMM): reduction dim % 32 == 0, output width in {64, 128} or a multiple of 256,
  * and for grad_weight N % 128 == 0. */

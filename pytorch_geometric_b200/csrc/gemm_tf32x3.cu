@@ -32,7 +32,7 @@ constexpr int kBM = 128;       // UMMA M
 // BK (fp32 elements per k-block) is a template parameter: 32 = one 128-byte swizzle row, 2 smem
 // stages of 96 KB (BN = 256); 16 = 64-byte rows (SWIZZLE_64B for K-major operands), 4 stages of 48 KB.
 constexpr int kAccStages = 2;
-constexpr int kGemmThreads = 384;
+constexpr int kGemmThreads = 512;   // 16 warps: TMA, MMA, 2 idle, splitter set 0 (4-7), epilogue (8-11), splitter set 1 (12-15)
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t s2u(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -91,6 +91,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// One lane of a fully converged warp (always the same one, so tcgen05.commit tracks the MMAs it issued).
+// The MMA issuer runs its loop WARP-WIDE and only the tcgen05 instructions sit under this predicate: with a
+// `if (lane == 0)` around the whole loop the loop state lives in vector registers, and the compiler wraps
+// every UTCHMMA (uniform-datapath operands) in an ELECT / BRA.U.ANY waterfall -- ~20 SASS instructions and
+// ~90 clk per MMA on a single warp, more than the 64 clk the MMA itself takes (profiles/r1_gemm_ts.md).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -267,62 +283,67 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int split = w / tiles_per_split;
-                const int kb0 = split * args.k_blocks_per_split;
-                const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
-                bar_wait(bar_tempty(acc), acc_phase ^ 1u);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w / tiles_per_split;
+            const int kb0 = split * args.k_blocks_per_split;
+            const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
+            bar_wait(bar_tempty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d = tmem_base + static_cast<uint32_t>(acc * BN);
+            uint32_t accumulate = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                bar_wait(bar_full(stage), phase);      // TMA bytes (incl. the pre-split B tiles) have landed
+                bar_wait(bar_split(stage), phase);     // hi/lo tiles written and fenced by the splitter
                 tc_fence_after();
-                const uint32_t d = tmem_base + static_cast<uint32_t>(acc * BN);
-                uint32_t accumulate = 0;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    bar_wait(bar_full(stage), phase);      // TMA bytes (incl. the pre-split B tiles) have landed
-                    bar_wait(bar_split(stage), phase);     // hi/lo tiles written and fenced by the splitter
-                    tc_fence_after();
-                    const uint32_t sa_hi = smem_base + stage * kStageBytes;
-                    const uint32_t sa_lo = sa_hi + kABytes;
-                    const uint32_t sb_hi = sa_hi + 2 * kABytes;
-                    const uint32_t sb_lo = sb_hi + kBBytes;
+                const uint32_t sa_hi = smem_base + stage * kStageBytes;
+                // descriptors of the k-block's first K = 8 slice; the next slice is a constant further along
+                // (K-major: 32 B along the 128-byte swizzle row; MN-major: the next 8 k-rows = 1024 B)
+                const uint64_t a_hi0 = smem_desc<A_MN, BK>(sa_hi, kSlab);
+                const uint64_t a_lo0 = smem_desc<A_MN, BK>(sa_hi + kABytes, kSlab);
+                const uint64_t b_hi0 = smem_desc<B_MN, BK>(sa_hi + 2 * kABytes, kSlab);
+                const uint64_t b_lo0 = smem_desc<B_MN, BK>(sa_hi + 2 * kABytes + kBBytes, kSlab);
+                if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < kBK / 8; ++j) {
-                        // K-major: 8 tf32 = 32 B further along the 128-byte swizzle row;
-                        // MN-major: the next group of 8 k-rows = 1024 B further.
-                        const uint32_t ao = A_MN ? j * 1024u : j * 32u;
-                        const uint32_t bo = B_MN ? j * 1024u : j * 32u;
-                        const uint64_t a_hi = smem_desc<A_MN, BK>(sa_hi + ao, kSlab);
-                        const uint64_t a_lo = smem_desc<A_MN, BK>(sa_lo + ao, kSlab);
-                        const uint64_t b_hi = smem_desc<B_MN, BK>(sb_hi + bo, kSlab);
-                        const uint64_t b_lo = smem_desc<B_MN, BK>(sb_lo + bo, kSlab);
+                        const uint64_t ao = static_cast<uint64_t>((A_MN ? j * 1024u : j * 32u) >> 4);
+                        const uint64_t bo = static_cast<uint64_t>((B_MN ? j * 1024u : j * 32u) >> 4);
                         if (!(args.debug & 2)) {
-                            umma_tf32(d, a_lo, b_hi, kIdesc, accumulate);     // small terms first
-                            umma_tf32(d, a_hi, b_lo, kIdesc, 1u);
-                            umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                            umma_tf32(d, a_lo0 + ao, b_hi0 + bo, kIdesc, accumulate);     // small terms first
+                            umma_tf32(d, a_hi0 + ao, b_lo0 + bo, kIdesc, 1u);
+                            umma_tf32(d, a_hi0 + ao, b_hi0 + bo, kIdesc, 1u);
                         } else {
-                            umma_tf32(d, a_hi, b_hi, kIdesc, accumulate);
+                            umma_tf32(d, a_hi0 + ao, b_hi0 + bo, kIdesc, accumulate);
                         }
                         accumulate = 1u;
                     }
                     umma_commit(bar_empty(stage));                        // frees the smem stage when the MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(bar_tfull(acc));                              // accumulator complete
-                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+                accumulate = 1u;
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
+            if (elect_one()) umma_commit(bar_tfull(acc));                 // accumulator complete
+            __syncwarp();
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== splitter (128 threads) =====================
-        const int tid = threadIdx.x - 128;
-        int stage = 0;
+    } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+        // ===================== splitter (2 sets of 128 threads, alternate k-blocks) =====================
+        const int set = warp >= 12 ? 1 : 0;
+        const int tid = (warp & 3) * 32 + lane;
+        int stage = 0, it = 0;
         uint32_t phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int split = w / tiles_per_split;
             const int kb0 = split * args.k_blocks_per_split;
             const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                if ((it & 1) != set) {
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    continue;
+                }
                 bar_wait(bar_full(stage), phase);
                 unsigned char* sa = smem_gen + stage * kStageBytes;
                 auto split_buf = [&](unsigned char* hi, unsigned char* lo, int bytes) {
@@ -343,7 +364,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // ===================== epilogue (128 threads, TMEM lane quadrant = warp % 4) =====================
         const int q = warp & 3;
         int acc = 0;
@@ -471,7 +492,8 @@ int get_option_gemm_prefetch(); // L2 prefetch distance in k-blocks for the stre
 
 static bool width_ok(int64_t w) { return w == 64 || w == 128 || (w > 0 && w % 256 == 0); }
 
-// TS path (A in TMEM): y[M, n_out] = a[M, k_red] . B, B pre-split, K-major or MN-major
+// TS path (A in TMEM): y[M, n_out] = a[M, k_red] . B, K-major or MN-major B; b_lo == nullptr: b_hi is the
+// unsplit matrix and the kernel splits the B tiles itself
 static int run_ts(const float* a, const float* b_hi, const float* b_lo, float* c, int64_t m, int64_t n_out, int64_t k_red,
                   bool b_mn, int64_t b_rows, int64_t b_cols, cudaStream_t s) {
     CUtensorMap ta, tbh, tbl, tc;
@@ -479,17 +501,22 @@ static int run_ts(const float* a, const float* b_hi, const float* b_lo, float* c
     if ((rc = make_map(&tc, c, m, n_out, n_out, false, 32, 32))) return rc;      // output boxes [32 rows x 32 cols]
     if ((rc = make_map(&ta, a, m, k_red, k_red, false, 32, kBM))) return rc;
     if ((rc = make_map(&tbh, b_hi, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
-    if ((rc = make_map(&tbl, b_lo, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
+    if ((rc = make_map(&tbl, b_lo ? b_lo : b_hi, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
     const int kb = static_cast<int>(k_red / 32);
     GemmArgs args{c, m, n_out, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n_out / kTsBN), kb, kb, 1, get_option_gemm_prefetch(), get_option_gemm_debug()};
-    return b_mn ? launch_gemm_ts<true>(ta, tbh, tbl, tc, args, s) : launch_gemm_ts<false>(ta, tbh, tbl, tc, args, s);
+    if (!b_lo) return b_mn ? launch_gemm_ts<true, true>(ta, tbh, tbl, tc, args, s) : launch_gemm_ts<false, true>(ta, tbh, tbl, tc, args, s);
+    return b_mn ? launch_gemm_ts<true, false>(ta, tbh, tbl, tc, args, s) : launch_gemm_ts<false, false>(ta, tbh, tbl, tc, args, s);
 }
 
 // y[M,N] = x[M,K] . w[N,K]^T
 template <int BK>
 static int run_forward(const float* x, const float* w_hi, const float* w_lo, float* y, int64_t m, int64_t n, int64_t k,
                        cudaStream_t s) {
-    if (get_option_gemm_mode() == 1 && n % kTsBN == 0) return run_ts(x, w_hi, w_lo, y, m, n, k, false, n, k, s);
+    if ((get_option_gemm_mode() == 1 || !w_lo) && n % kTsBN == 0) return run_ts(x, w_hi, w_lo, y, m, n, k, false, n, k, s);
+    if (!w_lo) {
+        set_error("linear_tf32x3: an unsplit weight (w_lo == NULL) needs an output width that is a multiple of %d", kTsBN);
+        return B200MP_ERR_UNSUPPORTED;
+    }
     const int bn = n >= 256 ? 256 : static_cast<int>(n);
     CUtensorMap ta, tbh, tbl;
     int rc;
@@ -506,7 +533,11 @@ static int run_forward(const float* x, const float* w_hi, const float* w_lo, flo
 template <int BK>
 static int run_grad_input(const float* g, const float* w_hi, const float* w_lo, float* gx, int64_t m, int64_t n, int64_t k,
                           cudaStream_t s) {
-    if (get_option_gemm_mode() == 1 && k % kTsBN == 0) return run_ts(g, w_hi, w_lo, gx, m, k, n, true, n, k, s);
+    if ((get_option_gemm_mode() == 1 || !w_lo) && k % kTsBN == 0) return run_ts(g, w_hi, w_lo, gx, m, k, n, true, n, k, s);
+    if (!w_lo) {
+        set_error("linear_grad_input_tf32x3: an unsplit weight (w_lo == NULL) needs an input width that is a multiple of %d", kTsBN);
+        return B200MP_ERR_UNSUPPORTED;
+    }
     const int bn = k >= 256 ? 256 : static_cast<int>(k);
     CUtensorMap ta, tbh, tbl;
     int rc;
@@ -567,7 +598,7 @@ extern "C" int b200mp_linear_tf32x3(const float* x, const float* w_hi, const flo
                                     int64_t k, void* stream) {
     B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
     if (m == 0) return B200MP_OK;
-    B200MP_CHECK_ARG(x && w_hi && w_lo && y && ok16(x) && ok16(w_hi) && ok16(w_lo) && ok16(y));
+    B200MP_CHECK_ARG(x && w_hi && y && ok16(x) && ok16(w_hi) && ok16(w_lo) && ok16(y));
     if (k % 32 != 0 || !width_ok(n) || m > 0x7fffffffLL) {
         set_error("linear_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
         return B200MP_ERR_UNSUPPORTED;
@@ -580,7 +611,7 @@ extern "C" int b200mp_linear_grad_input_tf32x3(const float* g, const float* w_hi
                                                int64_t n, int64_t k, void* stream) {
     B200MP_CHECK_ARG(m >= 0 && n > 0 && k > 0);
     if (m == 0) return B200MP_OK;
-    B200MP_CHECK_ARG(g && w_hi && w_lo && gx && ok16(g) && ok16(w_hi) && ok16(w_lo) && ok16(gx));
+    B200MP_CHECK_ARG(g && w_hi && gx && ok16(g) && ok16(w_hi) && ok16(w_lo) && ok16(gx));
     if (n % 32 != 0 || !width_ok(k) || m > 0x7fffffffLL) {
         set_error("linear_grad_input_tf32x3: unsupported shape m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
         return B200MP_ERR_UNSUPPORTED;

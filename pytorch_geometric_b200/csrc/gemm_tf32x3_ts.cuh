@@ -11,7 +11,11 @@
 //
 // Tile: BM = 128, BN = 128, BK = 32; 4 smem stages of 48 KB (A raw 16 KB + B_hi 16 KB + B_lo 16 KB);
 // TMEM: 2 accumulator stages x 128 columns + 4 A slots x (32 hi + 32 lo) columns = 512 columns.
-// A is K-major (row-major [M, K]); B is K-major or MN-major and pre-split (W_hi, W_lo).
+// A is K-major (row-major [M, K]); B is K-major or MN-major, either pre-split (W_hi, W_lo) or -- B_SPLIT --
+// loaded raw and split in place by the splitter warps.  Why B_SPLIT: every output tile re-reads its B tiles
+// from L2, and at M = 10^7 rows the kernel's L2 -> SM traffic (A twice, B_hi + B_lo per tile, C once: 70 GB
+// for the 256 x 256 layer) runs into the L2 slice throughput (~6300 B/clk chip-wide) before the tensor pipe
+// saturates; loading W once per tile instead of W_hi and W_lo removes 20 GB of it.
 #pragma once
 
 namespace b200mp {
@@ -50,7 +54,7 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uin
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool B_MN>
+template <bool B_MN, bool B_SPLIT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_hi,
                       const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_c,
@@ -60,7 +64,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr uint32_t kABytes = kBM * BK * 4;                  // raw fp32 A tile (K-major, 128B swizzle)
     constexpr uint32_t kBBytes = BN * BK * 4;
     constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;     // 48 KB
-    constexpr uint32_t kTxBytes = kStageBytes;
+    constexpr uint32_t kTxBytes = B_SPLIT ? kABytes + kBBytes : kStageBytes;
     constexpr uint32_t kAccCols = kAccStages * BN;              // 256
     constexpr uint32_t kASlotCols = 2 * BK;                     // hi | lo
     constexpr uint32_t kTmemCols = 512;
@@ -130,62 +134,76 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     const uint32_t sb_lo = sb_hi + kBBytes;
                     bar_expect_tx(bar_full(stage), kTxBytes);
                     tma_load_2d(sa, &tmap_a, kb * BK, m0, bar_full(stage));
+                    // B_SPLIT: tmap_b_hi describes the unsplit matrix; its tile lands in the hi buffer
                     if (B_MN) {
 #pragma unroll
                         for (int s = 0; s < BN / 32; ++s) {
                             tma_load_2d(sb_hi + s * kSlab, &tmap_b_hi, n0 + 32 * s, kb * BK, bar_full(stage));
-                            tma_load_2d(sb_lo + s * kSlab, &tmap_b_lo, n0 + 32 * s, kb * BK, bar_full(stage));
+                            if (!B_SPLIT) tma_load_2d(sb_lo + s * kSlab, &tmap_b_lo, n0 + 32 * s, kb * BK, bar_full(stage));
                         }
                     } else {
                         tma_load_2d(sb_hi, &tmap_b_hi, kb * BK, n0, bar_full(stage));
-                        tma_load_2d(sb_lo, &tmap_b_lo, kb * BK, n0, bar_full(stage));
+                        if (!B_SPLIT) tma_load_2d(sb_lo, &tmap_b_lo, kb * BK, n0, bar_full(stage));
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                bar_wait(bar_tempty(acc), acc_phase ^ 1u);
+        // MMA issuer: the loop runs warp-wide, one elected lane issues (see elect_one in gemm_tf32x3.cu)
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            bar_wait(bar_tempty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d = tmem_base + static_cast<uint32_t>(acc * BN);
+            uint32_t accumulate = 0;
+            for (int kb = 0; kb < args.k_blocks; ++kb) {
+                bar_wait(bar_full(stage), phase);
+                bar_wait(bar_split(stage), phase);
                 tc_fence_after();
-                const uint32_t d = tmem_base + static_cast<uint32_t>(acc * BN);
-                uint32_t accumulate = 0;
-                for (int kb = 0; kb < args.k_blocks; ++kb) {
-                    bar_wait(bar_full(stage), phase);
-                    bar_wait(bar_split(stage), phase);
-                    tc_fence_after();
-                    const uint32_t sb_hi = smem_base + stage * kStageBytes + kABytes;
-                    const uint32_t sb_lo = sb_hi + kBBytes;
-                    const uint32_t a_hi = tmem_a0 + static_cast<uint32_t>(stage) * kASlotCols;
-                    const uint32_t a_lo = a_hi + BK;
+                const uint32_t sb_hi = smem_base + stage * kStageBytes + kABytes;
+                const uint64_t b_hi0 = smem_desc<B_MN, BK>(sb_hi, kSlab);
+                const uint64_t b_lo0 = smem_desc<B_MN, BK>(sb_hi + kBBytes, kSlab);
+                const uint32_t a_hi = tmem_a0 + static_cast<uint32_t>(stage) * kASlotCols;
+                const uint32_t a_lo = a_hi + BK;
+                if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < BK / 8; ++j) {
-                        const uint32_t bo = B_MN ? j * 1024u : j * 32u;
-                        const uint64_t b_hi = smem_desc<B_MN, BK>(sb_hi + bo, kSlab);
-                        const uint64_t b_lo = smem_desc<B_MN, BK>(sb_lo + bo, kSlab);
-                        umma_tf32_ts(d, a_lo + j * 8, b_hi, kIdesc, accumulate);
-                        umma_tf32_ts(d, a_hi + j * 8, b_lo, kIdesc, 1u);
-                        umma_tf32_ts(d, a_hi + j * 8, b_hi, kIdesc, 1u);
+                        const uint64_t bo = static_cast<uint64_t>((B_MN ? j * 1024u : j * 32u) >> 4);
+                        umma_tf32_ts(d, a_lo + j * 8, b_hi0 + bo, kIdesc, accumulate);
+                        umma_tf32_ts(d, a_hi + j * 8, b_lo0 + bo, kIdesc, 1u);
+                        umma_tf32_ts(d, a_hi + j * 8, b_hi0 + bo, kIdesc, 1u);
                         accumulate = 1u;
                     }
                     umma_commit(bar_empty(stage));
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(bar_tfull(acc));
-                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+                accumulate = 1u;
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
+            if (elect_one()) umma_commit(bar_tfull(acc));
+            __syncwarp();
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if ((warp >= 4 && warp < 8) || warp >= 12) {
         // ===== splitter: smem row m (K-major, 128B swizzle) -> (hi, lo) -> TMEM lane m =====
+        // TWO sets of four warps (4-7 and 12-15) take alternate k-blocks.  One set was the kernel's critical
+        // path: its per-k-block chain (mbarrier wait -> LDS -> split -> tcgen05.st -> wait::st -> arrive,
+        // ~1100 clk) is longer than the 768 clk the twelve MMAs of a k-block need, so the MMA warp spent its
+        // time waiting on bar_split (profiles/r1_gemm_ts.md: 70 % tensor-pipe activity, 3 M retries on
+        // that barrier against 3 k on the TMA barrier).
+        const int set = warp >= 12 ? 1 : 0;
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        int stage = 0;
+        int stage = 0, it = 0;
         uint32_t phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            for (int kb = 0; kb < args.k_blocks; ++kb) {
+            for (int kb = 0; kb < args.k_blocks; ++kb, ++it) {
+                if ((it & 1) != set) {
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    continue;
+                }
                 bar_wait(bar_full(stage), phase);
                 const unsigned char* row = smem_gen + stage * kStageBytes + m * 128;
                 const uint32_t t_hi = tmem_a0 + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(stage) * kASlotCols;
@@ -205,13 +223,26 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     tmem_st16(t_hi + half * 16, hi);
                     tmem_st16(t_hi + BK + half * 16, lo);
                 }
+                if (B_SPLIT) {
+                    // raw B tile -> (hi in place, lo next to it): element-wise, so the swizzled layout is kept
+                    unsigned char* bh = smem_gen + stage * kStageBytes + kABytes;
+                    const int tid = m;
+#pragma unroll
+                    for (int off = tid * 16; off < static_cast<int>(kBBytes); off += 128 * 16) {
+                        const float4 v = *reinterpret_cast<const float4*>(bh + off);
+                        const float4 h = make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+                        *reinterpret_cast<float4*>(bh + off) = h;
+                        *reinterpret_cast<float4*>(bh + kBBytes + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> MMA (async proxy) reads
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 bar_arrive(bar_split(stage));
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         const int q = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -245,17 +276,17 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
         }
     }
-    if (warp >= 8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all output boxes written
+    if (warp >= 8 && warp < 12 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all output boxes written
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <bool B_MN>
+template <bool B_MN, bool B_SPLIT>
 static int launch_gemm_ts(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const CUtensorMap& tc,
                           const GemmArgs& args, cudaStream_t stream) {
     constexpr size_t smem = kTsStages * (kBM * 32 * 4 + 2 * kTsBN * 32 * 4) + 4 * 2 * 4096 + 256 + 1024;
-    auto kfn = gemm_tf32x3_ts_kernel<B_MN>;
+    auto kfn = gemm_tf32x3_ts_kernel<B_MN, B_SPLIT>;
     B200MP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int n_work = args.n_tiles_m * args.n_tiles_n;
     const int grid = n_work < num_sms() ? n_work : num_sms();

@@ -11,6 +11,8 @@ Two back ends, same fp32-level accuracy:
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 import torch.nn.functional as F
 from torch import Tensor
@@ -21,6 +23,16 @@ from ._lib import check, lib
 _BACKEND = "tf32x3"
 DEFAULT_GEMM_MODE = 1   # library default of b200mp_set_option("gemm_mode"): 0 = SS, 1 = TS (A operand in TMEM)
 DEFAULT_GEMM_PREFETCH = 0   # library default of b200mp_set_option("gemm_prefetch") (k-blocks ahead, 0 = off)
+_B_SPLIT = False            # True: pass W unsplit and let the kernel split its B tiles (w_lo == NULL in the C ABI)
+
+
+def set_b_split(on: bool) -> None:
+    global _B_SPLIT
+    _B_SPLIT = bool(on)
+
+
+def get_b_split() -> bool:
+    return _B_SPLIT
 
 
 def set_backend(name: str) -> None:
@@ -53,7 +65,15 @@ def split_tf32(w: Tensor):
     return hi, lo
 
 
-def linear_forward(x: Tensor, w_hi: Tensor, w_lo: Tensor, out: Tensor = None) -> Tensor:
+def prepare_weight(weight: Tensor):
+    """(w_hi, w_lo) for the kernels; (w, None) when the kernel splits B tiles itself."""
+    n, k = weight.shape
+    if _B_SPLIT and n % 128 == 0 and k % 128 == 0:
+        return weight.detach().contiguous(), None
+    return split_tf32(weight)
+
+
+def linear_forward(x: Tensor, w_hi: Tensor, w_lo: Optional[Tensor], out: Tensor = None) -> Tensor:
     m, k = x.shape
     n = w_hi.size(0)
     if out is None:
@@ -62,17 +82,17 @@ def linear_forward(x: Tensor, w_hi: Tensor, w_lo: Tensor, out: Tensor = None) ->
         if out.shape != (m, n) or out.dtype != torch.float32 or not out.is_contiguous():
             raise ValueError("out must be a contiguous fp32 [M, N] tensor")
         y = out
-    ops._timed("linear_tf32x3", 1, lib().b200mp_linear_tf32x3, x.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(),
+    ops._timed("linear_tf32x3", 1, lib().b200mp_linear_tf32x3, x.data_ptr(), w_hi.data_ptr(), ops._p(w_lo),
                y.data_ptr(), m, n, k, ops._stream())
     return y
 
 
-def linear_grad_input(g: Tensor, w_hi: Tensor, w_lo: Tensor) -> Tensor:
+def linear_grad_input(g: Tensor, w_hi: Tensor, w_lo: Optional[Tensor]) -> Tensor:
     m, n = g.shape
     k = w_hi.size(1)
     gx = torch.empty((m, k), dtype=torch.float32, device=g.device)
     ops._timed("linear_grad_input_tf32x3", 1, lib().b200mp_linear_grad_input_tf32x3, g.data_ptr(), w_hi.data_ptr(),
-               w_lo.data_ptr(), gx.data_ptr(), m, n, k, ops._stream())
+               ops._p(w_lo), gx.data_ptr(), m, n, k, ops._stream())
     return gx
 
 
@@ -98,7 +118,7 @@ class _LinearTF32x3(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor):
         x = x.contiguous()
-        w_hi, w_lo = split_tf32(weight)
+        w_hi, w_lo = prepare_weight(weight)
         ctx.save_for_backward(x, w_hi, w_lo)
         return linear_forward(x, w_hi, w_lo)
 

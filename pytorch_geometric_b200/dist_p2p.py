@@ -116,7 +116,7 @@ class _LinearInto(torch.autograd.Function):
     def forward(ctx, x: Tensor, weight: Tensor, out: Tensor):
         x = x.contiguous()
         if dense.get_backend() == "tf32x3" and dense.supported(x, weight):
-            w_hi, w_lo = dense.split_tf32(weight)
+            w_hi, w_lo = dense.prepare_weight(weight)
             ctx.save_for_backward(x, w_hi, w_lo)
             ctx.fast = True
             dense.linear_forward(x, w_hi, w_lo, out=out)

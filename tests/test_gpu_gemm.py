@@ -56,6 +56,40 @@ def test_linear_tf32x3_forward_and_grads(m, n, k, gemm_bk):
     assert torch.equal(gw, dense.linear_grad_weight(go, x))
 
 
+@pytest.mark.parametrize("m", [1, 129, 1000, 20011])
+@pytest.mark.parametrize("n,k", [(256, 256), (128, 256), (256, 128), (512, 256)])
+def test_unsplit_weight_gives_the_same_bits(m, n, k):
+    """w_lo == NULL: the kernel splits each B tile itself (hi in place, lo next to it).  The split is the same
+    arithmetic, so the results must be bit-identical to the pre-split path (TS mode, both B layouts)."""
+    from pytorch_geometric_b200 import ops
+    ops.set_option("gemm_mode", 1)
+    g = torch.Generator(device=DEV).manual_seed(m + n + k)
+    x = torch.randn(m, k, device=DEV, generator=g)
+    w = torch.randn(n, k, device=DEV, generator=g) / k ** 0.5
+    go = torch.randn(m, n, device=DEV, generator=g)
+    w_hi, w_lo = dense.split_tf32(w)
+    assert torch.equal(dense.linear_forward(x, w, None), dense.linear_forward(x, w_hi, w_lo))
+    assert torch.equal(dense.linear_grad_input(go, w, None), dense.linear_grad_input(go, w_hi, w_lo))
+    dense.set_b_split(True)
+    try:
+        assert dense.prepare_weight(w)[1] is None
+        conv = GCNConv(k, n).to(DEV)
+        ei = torch.randint(0, m, (2, 4 * m), device=DEV)
+        xr = x.clone().requires_grad_()
+        out = conv(xr, ei)
+        out.backward(go)
+        g1, gw1 = xr.grad.clone(), conv.lin.weight.grad.clone()
+        dense.set_b_split(False)
+        xr.grad = None
+        conv.zero_grad()
+        out2 = conv(xr, ei)
+        out2.backward(go)
+        assert torch.equal(out, out2) and torch.equal(g1, xr.grad) and torch.equal(gw1, conv.lin.weight.grad)
+    finally:
+        dense.set_b_split(False)
+        ops.set_option("gemm_mode", DEFAULT_GEMM_MODE)
+
+
 def test_tf32x3_is_fp32_class_not_tf32_class():
     """A single-pass TF32 product is ~1e-3 accurate; the 3x split must be ~100x better than that."""
     g = torch.Generator(device=DEV).manual_seed(0)
