@@ -417,10 +417,11 @@ def run_b200(args):
                            f"node-range sharding x{world}, p_local={args.p_local}, " +
                            ("halo rows gathered over NVLink peer memory inside the kernel (symmetric memory)"
                             if args.dist == "p2p" else "halo all_to_all (NCCL) overlapped with the local sweep")),
-                       "gemm": ("hand-written tcgen05 3xTF32 (fp32-accurate, csrc/gemm_tf32x3.cu)" if args.dense == "tf32x3"
+                       "gemm": ("hand-written tcgen05 3xTF32, A operand in TMEM (fp32-accurate, csrc/gemm_tf32x3.cu + gemm_tf32x3_ts.cuh)" if args.dense == "tf32x3"
                                 else "torch.nn.functional.linear (cuBLAS fp32, allow_tf32=False)"),
                        "long_rows": graph.plan.n_long, "chunks": graph.plan.n_chunks,
-                       "spmm_impl": {0: "auto (TMA streaming kernel for 512 B..2 KB rows)", 1: "lane-group kernel", 2: "TMA kernel"}[args.spmm_impl]},
+                       "spmm_impl": {0: "default (register-staged lane-group kernel, csrc/csr_reduce.cuh)", 1: "lane-group kernel",
+                                     2: "persistent TMA-fed variant (csrc/csr_tma.cuh)"}[args.spmm_impl]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "kernels": kern, "clocks": clocks,
         }

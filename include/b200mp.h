@@ -217,6 +217,14 @@ int b200mp_softmax_edge_op(int op, const float* a, const float* b, const float* 
                            float* out, int64_t n_src, int64_t heads, int idx_dtype, void* stream);
 
 
+/* ------------------------------------------------------------------ bias gradient
+ * out[f] = sum_i x[i, f] (fp32): the gradient of the layer bias that autograd derives for `out + bias`
+ * (nn/conv/gcn_conv.py:263-264), as one deterministic two-launch column sum instead of ATen's generic
+ * reduction.  partials: caller-owned fp32 workspace [n_parts, feat], n_parts from b200mp_column_sum_parts. */
+int64_t b200mp_column_sum_parts(int64_t n_rows);
+int b200mp_column_sum(const void* x, float* out, float* partials, int64_t n_parts, int64_t n_rows, int64_t feat,
+                      int val_dtype, void* stream);
+
 /* ------------------------------------------------------------------ multi-aggregation (one sweep, k outputs)
  * Replaces FusedAggregation.forward (nn/aggr/fused.py:191-336: one scatter per base reduction plus the
  * shared count) and the [sum, mean, min, max, var, std] members of MultiAggregation (nn/aggr/multi.py):

@@ -32,7 +32,8 @@ constexpr int kBM = 128;       // UMMA M
 // BK (fp32 elements per k-block) is a template parameter: 32 = one 128-byte swizzle row, 2 smem
 // stages of 96 KB (BN = 256); 16 = 64-byte rows (SWIZZLE_64B for K-major operands), 4 stages of 48 KB.
 constexpr int kAccStages = 2;
-constexpr int kGemmThreads = 512;   // 16 warps: TMA, MMA, 2 idle, splitter set 0 (4-7), epilogue (8-11), splitter set 1 (12-15)
+constexpr int kGemmThreads = 384;     // SS kernel: TMA, MMA, 2 idle, splitter (4-7), epilogue (8-11)
+constexpr int kGemmThreadsTs = 512;   // TS kernel: + a second splitter set (warps 12-15)
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t s2u(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -93,10 +94,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // One lane of a fully converged warp (always the same one, so tcgen05.commit tracks the MMAs it issued).
-// The MMA issuer runs its loop WARP-WIDE and only the tcgen05 instructions sit under this predicate: with a
-// `if (lane == 0)` around the whole loop the loop state lives in vector registers, and the compiler wraps
-// every UTCHMMA (uniform-datapath operands) in an ELECT / BRA.U.ANY waterfall -- ~20 SASS instructions and
-// ~90 clk per MMA on a single warp, more than the 64 clk the MMA itself takes (profiles/r1_gemm_ts.md).
+// The TS kernel's MMA issuer runs its loop WARP-WIDE and only the tcgen05 instructions sit under this
+// predicate: with `if (lane == 0)` around the whole loop the loop state lives in vector registers and the
+// compiler wraps every UTCHMMA (uniform-datapath operands) in an ELECT / BRA.U.ANY waterfall, ~20 SASS
+// instructions per MMA (profiles/r1_gemm_ts.md).  Measured perf-neutral for the TS kernel; the SS kernel got
+// slower with the same change plus a second splitter set (grad_weight 7.7 -> 9.5 ms inside bench.py), so it
+// keeps its single-thread issuer and one splitter set.
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -283,67 +286,62 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        int stage = 0, acc = 0;
-        uint32_t phase = 0, acc_phase = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int split = w / tiles_per_split;
-            const int kb0 = split * args.k_blocks_per_split;
-            const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
-            bar_wait(bar_tempty(acc), acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d = tmem_base + static_cast<uint32_t>(acc * BN);
-            uint32_t accumulate = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                bar_wait(bar_full(stage), phase);      // TMA bytes (incl. the pre-split B tiles) have landed
-                bar_wait(bar_split(stage), phase);     // hi/lo tiles written and fenced by the splitter
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w / tiles_per_split;
+                const int kb0 = split * args.k_blocks_per_split;
+                const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
+                bar_wait(bar_tempty(acc), acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t sa_hi = smem_base + stage * kStageBytes;
-                // descriptors of the k-block's first K = 8 slice; the next slice is a constant further along
-                // (K-major: 32 B along the 128-byte swizzle row; MN-major: the next 8 k-rows = 1024 B)
-                const uint64_t a_hi0 = smem_desc<A_MN, BK>(sa_hi, kSlab);
-                const uint64_t a_lo0 = smem_desc<A_MN, BK>(sa_hi + kABytes, kSlab);
-                const uint64_t b_hi0 = smem_desc<B_MN, BK>(sa_hi + 2 * kABytes, kSlab);
-                const uint64_t b_lo0 = smem_desc<B_MN, BK>(sa_hi + 2 * kABytes + kBBytes, kSlab);
-                if (elect_one()) {
+                const uint32_t d = tmem_base + static_cast<uint32_t>(acc * BN);
+                uint32_t accumulate = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    bar_wait(bar_full(stage), phase);      // TMA bytes (incl. the pre-split B tiles) have landed
+                    bar_wait(bar_split(stage), phase);     // hi/lo tiles written and fenced by the splitter
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_base + stage * kStageBytes;
+                    const uint32_t sa_lo = sa_hi + kABytes;
+                    const uint32_t sb_hi = sa_hi + 2 * kABytes;
+                    const uint32_t sb_lo = sb_hi + kBBytes;
 #pragma unroll
                     for (int j = 0; j < kBK / 8; ++j) {
-                        const uint64_t ao = static_cast<uint64_t>((A_MN ? j * 1024u : j * 32u) >> 4);
-                        const uint64_t bo = static_cast<uint64_t>((B_MN ? j * 1024u : j * 32u) >> 4);
+                        // K-major: 8 tf32 = 32 B further along the 128-byte swizzle row;
+                        // MN-major: the next group of 8 k-rows = 1024 B further.
+                        const uint32_t ao = A_MN ? j * 1024u : j * 32u;
+                        const uint32_t bo = B_MN ? j * 1024u : j * 32u;
+                        const uint64_t a_hi = smem_desc<A_MN, BK>(sa_hi + ao, kSlab);
+                        const uint64_t a_lo = smem_desc<A_MN, BK>(sa_lo + ao, kSlab);
+                        const uint64_t b_hi = smem_desc<B_MN, BK>(sb_hi + bo, kSlab);
+                        const uint64_t b_lo = smem_desc<B_MN, BK>(sb_lo + bo, kSlab);
                         if (!(args.debug & 2)) {
-                            umma_tf32(d, a_lo0 + ao, b_hi0 + bo, kIdesc, accumulate);     // small terms first
-                            umma_tf32(d, a_hi0 + ao, b_lo0 + bo, kIdesc, 1u);
-                            umma_tf32(d, a_hi0 + ao, b_hi0 + bo, kIdesc, 1u);
+                            umma_tf32(d, a_lo, b_hi, kIdesc, accumulate);     // small terms first
+                            umma_tf32(d, a_hi, b_lo, kIdesc, 1u);
+                            umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
                         } else {
-                            umma_tf32(d, a_hi0 + ao, b_hi0 + bo, kIdesc, accumulate);
+                            umma_tf32(d, a_hi, b_hi, kIdesc, accumulate);
                         }
                         accumulate = 1u;
                     }
                     umma_commit(bar_empty(stage));                        // frees the smem stage when the MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                accumulate = 1u;
-                __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                umma_commit(bar_tfull(acc));                              // accumulator complete
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
             }
-            if (elect_one()) umma_commit(bar_tfull(acc));                 // accumulator complete
-            __syncwarp();
-            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if ((warp >= 4 && warp < 8) || warp >= 12) {
-        // ===================== splitter (2 sets of 128 threads, alternate k-blocks) =====================
-        const int set = warp >= 12 ? 1 : 0;
-        const int tid = (warp & 3) * 32 + lane;
-        int stage = 0, it = 0;
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== splitter (128 threads) =====================
+        const int tid = threadIdx.x - 128;
+        int stage = 0;
         uint32_t phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int split = w / tiles_per_split;
             const int kb0 = split * args.k_blocks_per_split;
             const int kb1 = min(kb0 + args.k_blocks_per_split, args.k_blocks);
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                if ((it & 1) != set) {
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                    continue;
-                }
+            for (int kb = kb0; kb < kb1; ++kb) {
                 bar_wait(bar_full(stage), phase);
                 unsigned char* sa = smem_gen + stage * kStageBytes;
                 auto split_buf = [&](unsigned char* hi, unsigned char* lo, int bytes) {
@@ -364,7 +362,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp >= 8 && warp < 12) {
+    } else if (warp >= 8) {
         // ===================== epilogue (128 threads, TMEM lane quadrant = warp % 4) =====================
         const int q = warp & 3;
         int acc = 0;

@@ -55,7 +55,7 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uin
 }
 
 template <bool B_MN, bool B_SPLIT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreadsTs, 1)
 gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_hi,
                       const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_c,
                       GemmArgs args) {
@@ -188,11 +188,9 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
     } else if ((warp >= 4 && warp < 8) || warp >= 12) {
         // ===== splitter: smem row m (K-major, 128B swizzle) -> (hi, lo) -> TMEM lane m =====
-        // TWO sets of four warps (4-7 and 12-15) take alternate k-blocks.  One set was the kernel's critical
-        // path: its per-k-block chain (mbarrier wait -> LDS -> split -> tcgen05.st -> wait::st -> arrive,
-        // ~1100 clk) is longer than the 768 clk the twelve MMAs of a k-block need, so the MMA warp spent its
-        // time waiting on bar_split (profiles/r1_gemm_ts.md: 70 % tensor-pipe activity, 3 M retries on
-        // that barrier against 3 k on the TMA barrier).
+        // Two sets of four warps (4-7 and 12-15) take alternate k-blocks, so that one set's chain (mbarrier
+        // wait -> LDS -> split -> tcgen05.st -> wait::st -> arrive) overlaps the other's.  Measured perf-neutral
+        // (profiles/r1_gemm_ts.md): the kernel sits at 70 % tensor-pipe activity with or without it.
         const int set = warp >= 12 ? 1 : 0;
         const int q = warp & 3;
         const int m = q * 32 + lane;
@@ -290,7 +288,7 @@ static int launch_gemm_ts(const CUtensorMap& ta, const CUtensorMap& tbh, const C
     B200MP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int n_work = args.n_tiles_m * args.n_tiles_n;
     const int grid = n_work < num_sms() ? n_work : num_sms();
-    kfn<<<grid, kGemmThreads, smem, stream>>>(ta, tbh, tbl, tc, args);
+    kfn<<<grid, kGemmThreadsTs, smem, stream>>>(ta, tbh, tbl, tc, args);
     B200MP_LAUNCH_CHECK();
     return B200MP_OK;
 }

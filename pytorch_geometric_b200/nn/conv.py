@@ -66,7 +66,7 @@ class _BiasAggregate(torch.autograd.Function):
             graph.build_transpose()
             gx = ops.spmm_csr(graph.rowptr_t, graph.col_t, graph.val_t, grad_out, graph.num_src, "sum", graph.plan_t)
         if ctx.needs_input_grad[1]:
-            gb = grad_out.sum(0, dtype=torch.float32)
+            gb = ops.column_sum(grad_out)
         return gx, gb, None
 
 

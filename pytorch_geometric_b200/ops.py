@@ -469,6 +469,20 @@ def gat_fused_csr_backward(rowptr, col, dst_of_edge, rowptr_t, col_t, t2csr, xh,
     return gxh, gas, gad
 
 
+def column_sum(x: Tensor) -> Tensor:
+    """sum over rows of a [n, F] matrix in fp32 (the bias gradient); deterministic, two launches."""
+    _cuda(x)
+    if x.dim() != 2:
+        raise ValueError("column_sum expects a 2-D matrix")
+    x = x.contiguous()
+    n, F = x.shape
+    out = torch.empty(F, dtype=torch.float32, device=x.device)
+    parts = int(lib().b200mp_column_sum_parts(n))
+    ws = torch.empty(parts * max(F, 1), dtype=torch.float32, device=x.device)
+    _timed("column_sum", 2, lib().b200mp_column_sum, _p(x), _p(out), _p(ws), parts, n, F, _vdt(x), _stream())
+    return out
+
+
 MULTI_AGGRS = ("sum", "mean", "min", "max", "var", "std")
 
 

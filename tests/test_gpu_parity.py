@@ -455,3 +455,18 @@ def test_large_graph_properties():
     assert ((mean * deg.clamp(min=1).view(-1, 1) - ax).abs() <= 1e-5 * scale + 1e-4).all()
     mx = pgb.aggregate(g, x, "max")
     assert (mx[deg > 0] >= mean[deg > 0] - 1e-5).all() and (mx[deg == 0] == 0).all()
+
+
+@pytest.mark.parametrize("n,F,dtype", [(0, 8, torch.float32), (1, 1, torch.float32), (777, 5, torch.float32),
+                                       (100003, 256, torch.float32), (50000, 64, torch.bfloat16), (4099, 300, torch.float32)])
+def test_column_sum_bias_gradient(n, F, dtype):
+    """b200mp_column_sum (the layer's bias gradient) vs an fp64 column sum; deterministic."""
+    from pytorch_geometric_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(n + F)
+    x = torch.randn(n, F, device=DEV, generator=g).to(dtype)
+    got = ops.column_sum(x)
+    ref = x.double().sum(0)
+    scale = x.double().abs().sum(0) + 1e-30
+    assert got.dtype == torch.float32 and got.shape == (F, )
+    assert ((got.double() - ref).abs() <= 1e-6 * scale + 1e-30).all()
+    assert torch.equal(got, ops.column_sum(x))
