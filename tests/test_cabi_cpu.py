@@ -53,3 +53,41 @@ def test_state_dict_layout_matches_reference_layers():
     assert set(SAGEConv(8, 16).state_dict()) == {"lin_l.weight", "lin_l.bias", "lin_r.weight"}
     sd = RGCNConv(8, 16, 3).state_dict()
     assert sd["weight"].shape == (3, 8, 16) and sd["root"].shape == (8, 16) and sd["bias"].shape == (16, )
+
+
+def test_fused_and_multi_aggregation_argument_errors_match_reference_messages():
+    # nn/aggr/fused.py:87-110 and multi.py:52-70,101-110: validated before anything touches the device
+    from pytorch_geometric_b200.nn import FusedAggregation, MultiAggregation, StdAggregation, aggregation_resolver
+    with pytest.raises(ValueError, match="should be a list or tuple"):
+        FusedAggregation("sum")
+    with pytest.raises(ValueError, match="should not be empty"):
+        FusedAggregation([])
+    with pytest.raises(ValueError, match="not fusable"):
+        FusedAggregation(["sum", "softmax"])
+    f = FusedAggregation(["sum", aggregation_resolver("std", semi_grad=True), "max"])
+    assert f.names == ["sum", "std", "max"] and f.semi_grad and repr(f) == "FusedAggregation()"
+    with pytest.raises(ValueError, match="should be a list or tuple"):
+        MultiAggregation("sum")
+    with pytest.raises(ValueError, match="should not be empty"):
+        MultiAggregation([])
+    with pytest.raises(ValueError, match="invalid length"):
+        MultiAggregation(["sum", "max"], aggrs_kwargs=[{}])
+    with pytest.raises(ValueError, match="Multiple aggregations are required"):
+        MultiAggregation(["sum"], mode="proj", mode_kwargs=dict(in_channels=4, out_channels=2))
+    with pytest.raises(ValueError, match="must have `in_channels` and `out_channels`"):
+        MultiAggregation(["sum", "max"], mode="proj")
+    m = MultiAggregation(["mean", "min", "max", "std"])
+    assert m.get_out_channels(16) == 64 and m.is_fused == [True] * 4
+    assert isinstance(m.aggrs[3], StdAggregation)
+    assert MultiAggregation(["sum", "softmax"], mode="proj", mode_kwargs=dict(in_channels=4, out_channels=3)).get_out_channels(4) == 3
+    # no CPU fallback here either
+    with pytest.raises(RuntimeError, match="CUDA"):
+        f(torch.randn(4, 8), torch.tensor([0, 1, 1, 3]), dim_size=4)
+
+
+def test_multi_aggr_wrapper_rejects_unknown_names_without_a_gpu():
+    from pytorch_geometric_b200 import functional as Fn
+    with pytest.raises(ValueError, match="cannot fuse aggregation 'mul'"):
+        Fn.multi_aggregate((torch.zeros(2, dtype=torch.long), torch.zeros(1, dtype=torch.long)), torch.randn(1, 4), ["sum", "mul"])
+    with pytest.raises(ValueError, match="duplicate"):
+        Fn.multi_aggregate((torch.zeros(2, dtype=torch.long), torch.zeros(1, dtype=torch.long)), torch.randn(1, 4), ["sum", "add"])
