@@ -61,7 +61,7 @@ def supported(x: Tensor, weight: Tensor) -> bool:
 def split_tf32(w: Tensor):
     w = w.detach().contiguous()
     hi, lo = torch.empty_like(w), torch.empty_like(w)
-    check(lib().b200mp_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), ops._stream()), "split_tf32")
+    ops._timed("split_tf32", 1, lib().b200mp_split_tf32, w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), ops._stream())
     return hi, lo
 
 
