@@ -1,12 +1,15 @@
 """In-tree build of libb200mp.so (the C-ABI library) with nvcc for sm_100a.
 
 No torch involvement: the library only depends on the CUDA runtime (statically linked), so the
-same .so serves Python (ctypes), C, C++ or any FFI.  Objects are rebuilt when a source or header
-is newer; the .so lands in pytorch_geometric_b200/lib/ and travels to the GPU box with the repo
-snapshot (it is git-ignored, not gpurun-ignored).
+same .so serves Python (ctypes), C, C++ or any FFI.  The .so lands in pytorch_geometric_b200/lib/ next to
+a stamp file holding the SHA-256 of every source, header and compiler flag it was built from, and travels
+to the GPU box with the repo snapshot (both are git-ignored, not gpurun-ignored).  Staleness is decided by
+that fingerprint, NOT by file times: a snapshot copy does not keep mtimes in any useful order, and a
+spurious rebuild costs minutes of nvcc on the GPU box.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -18,6 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.environ.get("B200MP_OBJ_DIR", os.path.join("/tmp", f"b200mp_build_{os.getuid()}"))  # objects stay out of tree
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200mp.so")
+STAMP = os.path.join(LIBDIR, "libb200mp.sha256")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -38,17 +42,34 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _headers_mtime() -> float:
+def _headers():
     hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hs.append(os.path.join(INCLUDE, "b200mp.h"))
-    return max(os.path.getmtime(h) for h in hs)
+    return sorted(hs)
+
+
+def _headers_mtime() -> float:
+    return max(os.path.getmtime(h) for h in _headers())
+
+
+def fingerprint() -> str:
+    """SHA-256 over the compiler flags and the contents of every source and header."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in sources() + _headers():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in sources()) or _headers_mtime() > t
+    try:
+        with open(STAMP) as fh:
+            return fh.read().strip() != fingerprint()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -79,6 +100,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(STAMP, "w") as fh:
+        fh.write(fingerprint() + "\n")
     return LIB
 
 

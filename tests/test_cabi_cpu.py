@@ -91,3 +91,30 @@ def test_multi_aggr_wrapper_rejects_unknown_names_without_a_gpu():
         Fn.multi_aggregate((torch.zeros(2, dtype=torch.long), torch.zeros(1, dtype=torch.long)), torch.randn(1, 4), ["sum", "mul"])
     with pytest.raises(ValueError, match="duplicate"):
         Fn.multi_aggregate((torch.zeros(2, dtype=torch.long), torch.zeros(1, dtype=torch.long)), torch.randn(1, 4), ["sum", "add"])
+
+
+def test_prebuilt_library_is_matched_by_content_not_by_file_time():
+    """The .so built here travels to the GPU box in a snapshot whose file times carry no meaning: staleness
+    is decided by a fingerprint of the sources, so touching a file must not trigger minutes of nvcc there."""
+    import os
+
+    from pytorch_geometric_b200 import _build
+    _build.build()
+    assert not _build.needs_build()
+    src = _build.sources()[0]
+    st = os.stat(src)
+    try:
+        os.utime(src)                                     # newer than the .so now
+        assert not _build.needs_build()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    with open(_build.STAMP) as fh:
+        good = fh.read()
+    try:
+        with open(_build.STAMP, "w") as fh:
+            fh.write("0" * 64 + "\n")
+        assert _build.needs_build()                       # a different fingerprint does
+    finally:
+        with open(_build.STAMP, "w") as fh:
+            fh.write(good)
+    assert not _build.needs_build()
