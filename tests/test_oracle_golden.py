@@ -213,3 +213,69 @@ def test_fused_aggregation_empty_input():
     # test/nn/aggr/test_fused.py:46-55: no messages at all -> zeros of shape [dim_size, F] per aggregation
     outs = O.fused_aggregation(np.zeros((0, 6), np.float32), np.zeros(0, np.int64), 5, ["mean", "var", "std"])
     assert all(o.shape == (5, 6) and float(np.abs(o).sum()) == 0.0 for o in outs)
+
+
+# ---------------------------------------------------------------- more of the reference's own known-answer tests
+def test_softmax_matches_dense_softmax_forward_and_backward():
+    # test/utils/test_softmax.py:30-45: groups of two rows == dense softmax over dim 1, same for the gradient of mean()
+    rng = np.random.default_rng(3)
+    src = rng.random((4, 8)).astype(np.float32)
+    index = np.array([0, 0, 1, 1])
+    out = O.softmax(src, index, 2)
+    d = src.reshape(2, 2, 8).astype(np.float64)
+    e = np.exp(d - d.max(1, keepdims=True))
+    dense = e / e.sum(1, keepdims=True)
+    assert_close(out, dense.reshape(4, 8), rtol=1e-6, atol=1e-7)
+    g = np.full((4, 8), 1.0 / 32, np.float32)                       # d mean() / d out
+    dense_grad = dense * (g.reshape(2, 2, 8) - (g.reshape(2, 2, 8) * dense).sum(1, keepdims=True))
+    assert_close(O.softmax_backward(g, out, index, 2), dense_grad.reshape(4, 8), rtol=1e-4, atol=1e-8)
+
+
+def test_softmax_single_group_is_plain_softmax():
+    # test/utils/test_softmax.py:48-62 (dim = 0 cases)
+    rng = np.random.default_rng(4)
+    for shape in ((4, ), (4, 16)):
+        src = rng.standard_normal(shape).astype(np.float32)
+        d = src.astype(np.float64)
+        e = np.exp(d - d.max(0, keepdims=True))
+        assert_close(O.softmax(src, np.zeros(4, np.int64), 1).reshape(shape), e / e.sum(0, keepdims=True), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("red", ["sum", "mean"])
+def test_spmm_basic_equals_dense_matmul(red):
+    # test/utils/test_spmm.py:18-38, including the isolated-node case for `mean`
+    rng = np.random.default_rng(5)
+    for zero_row in (False, True):
+        a = rng.standard_normal((5, 4)).astype(np.float32)
+        if zero_row:
+            a[0] = 0.0
+        other = rng.standard_normal((4, 8)).astype(np.float32)
+        rows, cols = np.nonzero(a)
+        rowptr = O.index2ptr(rows, 5)
+        out = O.spmm_csr(rowptr, cols, a[rows, cols], other, red)
+        want = a.astype(np.float64) @ other.astype(np.float64)
+        if red == "mean":
+            # to_sparse_csr drops explicit zeros, so the mean divides by the stored entries per row (4, or 1 when empty)
+            want = want / np.maximum(np.diff(rowptr), 1)[:, None]
+        assert out.shape == (5, 8)
+        assert_close(out, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("aggr", ["mean", "sum", "max", "min", "var", "std"])
+def test_basic_aggregation_index_equals_ptr(aggr):
+    # test/nn/aggr/test_basic.py:35-63 (index and ptr give the same answer) and :66-75 (var against its definition)
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((6, 16)).astype(np.float32)
+    index = np.array([0, 0, 1, 1, 1, 2])
+    ptr = np.array([0, 2, 5, 6])
+    if aggr in ("var", "std"):
+        out = O.fused_aggregation(x, index, 3, [aggr])[0]
+        mean = O.scatter(x, index, 3, "mean")
+        var = O.scatter(((x - mean[index]) ** 2).astype(np.float32), index, 3, "mean")
+        want = var if aggr == "var" else np.where(np.sqrt(np.maximum(var, 1e-5)) <= np.sqrt(1e-5), 0, np.sqrt(np.maximum(var, 1e-5)))
+        # E[x^2] - mean^2 cancels: the reference's own test allows 1e-6 on var, which is ~1e-5 on a small std
+        assert_close(out, want, rtol=1e-4, atol=1e-6 if aggr == "var" else 2e-5)
+    else:
+        out = O.scatter(x, index, 3, aggr)
+        assert out.shape == (3, 16)
+        assert_close(out, O.segment(x, ptr, aggr), rtol=1e-6, atol=1e-7)
