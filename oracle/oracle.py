@@ -323,3 +323,30 @@ def fused_aggregation_backward(grads, x, index, N, aggrs, semi_grad=False):
         if not semi_grad:
             gx += 2.0 * x.astype(np.float64) * (gvar / cnt)[index]
     return gx.astype(np.float32)
+
+
+def remove_then_add_self_loops(row, col, N):
+    """torch_geometric/utils/loop.py:71-131 + 382-492 as GATConv/GATv2Conv call them (gat_conv.py:342-346,
+    gatv2_conv.py:310-316): every existing loop is dropped, then one loop per node is appended in node order."""
+    row, col = _i(row), _i(col)
+    keep = row != col
+    loops = np.arange(N, dtype=np.int64)
+    return np.concatenate([row[keep], loops]), np.concatenate([col[keep], loops])
+
+
+def gatv2_attention(x_l, x_r, att, row, col, slope=0.2, add_self_loops=True):
+    """torch_geometric/nn/conv/gatv2_conv.py:310-331,356-378 -- GATv2Conv after the two linear maps:
+    e = (leaky_relu(x_r[i] + x_l[j]) * att).sum(-1) per head, alpha = softmax over the in-edges of i
+    (utils/_softmax.py:82-88), out[i] = sum_j alpha * x_l[j].  x_l, x_r: [N, H, C]; att: [H, C].
+    Groundwork for SURVEY section 8(f) rank 2 (no CUDA path yet).  Returns (out [N, H*C], alpha [E', H], row', col')."""
+    x_l, x_r, att = _f(x_l), _f(x_r), _f(att)
+    N, H, C = x_l.shape
+    row, col = _i(row), _i(col)
+    if add_self_loops:
+        row, col = remove_then_add_self_loops(row, col, N)
+    s = (x_r[col] + x_l[row]).astype(np.float32)
+    s = np.where(s > 0, s, np.float32(slope) * s).astype(np.float32)
+    e = (s * att[None]).astype(np.float32).sum(-1, dtype=np.float32)
+    alpha = softmax(e, col, N)
+    msg = (x_l[row] * alpha[:, :, None]).astype(np.float32).reshape(row.size, H * C)
+    return scatter(msg, col, N, "sum"), alpha, row, col

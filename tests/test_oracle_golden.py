@@ -279,3 +279,20 @@ def test_basic_aggregation_index_equals_ptr(aggr):
         out = O.scatter(x, index, 3, aggr)
         assert out.shape == (3, 16)
         assert_close(out, O.segment(x, ptr, aggr), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["sep", "shared"])
+def test_gatv2_attention_groundwork(tag):
+    """SURVEY section 8(f) rank 2 (next row, no CUDA path yet): the oracle's GATv2 restatement is already pinned
+    to the reference's GATv2Conv (tests/golden/make_golden_gatv2.py), forward incl. the attention weights."""
+    g = load_golden("gatv2")
+    H, C = int(g["H"]), int(g["C"])
+    x = g["x"]
+    x_l = (x @ g[f"{tag}_lin_l_w"].T + g[f"{tag}_lin_l_b"]).astype(np.float32).reshape(-1, H, C)
+    x_r = (x @ g[f"{tag}_lin_r_w"].T + g[f"{tag}_lin_r_b"]).astype(np.float32).reshape(-1, H, C)
+    out, alpha, row, col = O.gatv2_attention(x_l, x_r, g[f"{tag}_att"], g["ei"][0], g["ei"][1])
+    assert np.array_equal(np.stack([row, col]), g[f"{tag}_ei2"])          # remove + add self loops, same edge order
+    assert_close(alpha, g[f"{tag}_alpha"], rtol=1e-5, atol=1e-7)
+    assert_close(out + g[f"{tag}_bias"], g[f"{tag}_out"], rtol=1e-5, atol=1e-6)
+    sums = np.zeros((x.shape[0], H)); np.add.at(sums, col, alpha)
+    assert_close(sums, np.ones_like(sums), rtol=1e-5, atol=0)            # every node has its self loop
