@@ -20,8 +20,9 @@
  *    enqueue work; they never synchronise unless documented.
  *  - return value: 0 on success, a negative B200MP_ERR_* code otherwise.  Nothing throws
  *    across the ABI.  A kernel cannot raise: out-of-range indices are undefined behaviour
- *    unless b200mp_validate_index() is called first (the reference's "valid indices" IndexError,
- *    nn/conv/message_passing.py:269-290, is produced by the host-side mirror from that result).
+ *    unless the caller checks them first with b200mp_index_stats() (min / max / sortedness in one
+ *    pass); the host-side mirror raises the reference's "valid indices" IndexError
+ *    (nn/conv/message_passing.py:269-290) from that result.
  */
 #ifndef B200MP_H_
 #define B200MP_H_

@@ -118,3 +118,18 @@ def test_prebuilt_library_is_matched_by_content_not_by_file_time():
         with open(_build.STAMP, "w") as fh:
             fh.write(good)
     assert not _build.needs_build()
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/b200mp.h is the boundary: it must compile as C99 and as C++ with nothing but <stdint.h> (no torch types)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "b200mp.h"\nint main(void) { return b200mp_version() == 0; }\n')
+    inc = os.path.join(root, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+    text = open(os.path.join(inc, "b200mp.h")).read()
+    assert "#include <torch" not in text and "at::Tensor" not in text and "c10::" not in text
