@@ -92,6 +92,30 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers are first-touched
+    in node-local memory (at N = 8, eight 10 GB/step H2D streams from one node's DRAM and across the socket
+    interconnect halved the end-to-end rate).  Returns the node id or None when the topology cannot be read."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def synth_graph(num_nodes: int, num_edges: int, seed: int, device, lo: int = 0, total_nodes=None,
                 p_local: float = 1.0):
     """Seeded synthetic power-law graph: destination in-degrees follow a truncated
@@ -126,7 +150,10 @@ def traffic_bytes(args):
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path) and (args.nodes, args.edges, args.feat) == (10_000_000, 100_000_000, 256):
         with open(path) as f:
-            return json.load(f)["spmm_csr_bytes_per_launch"]
+            t = json.load(f)
+        if "spmm_csr_fwd_bytes" in t:
+            return {"fwd": t["spmm_csr_fwd_bytes"], "bwd": t["spmm_csr_bwd_bytes"], "mean": t["spmm_csr_bytes_per_launch"]}
+        return t["spmm_csr_bytes_per_launch"]
     return None
 
 
@@ -138,62 +165,94 @@ def pass_bytes(E_prime: int, N: int, F: int, s: int = 4, b_idx: int = 4, b_w: in
 
 
 # --------------------------------------------------------------------------- the CPU reference arm
-def run_reference(args):
-    """`--impl reference`: the reference's own CPU path (ATen call sequence of GCNConv on a [2,E]
-    tensor, oracle/ref_aten.py) timed on the host cores on a bounded sample of the workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import ref_aten
-    torch.manual_seed(0)
+def workload_config(args, world: int) -> dict:
+    """The workload both arms are quoted on (identical dict in the b200 and the reference line)."""
+    N, E, F = args.nodes, args.edges, args.feat
+    return {"workload": f"GCNConv({F},{F}) fwd+bwd, power-law synthetic graph (in-degree exponent 2.1, uniform sources), "
+                        f"N={N} nodes and E={E} edges per GPU, fp32, graph cached (cached=True)",
+            "nodes_per_gpu": N, "edges_per_gpu": E, "feat": F, "layers": 1, "n_gpus": world}
+
+
+def _import_reference():
+    """The UNMODIFIED reference package installed by baseline/install_ref.sh (git-ignored, travels with gpurun)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref, "torch_geometric")):
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        import torch_geometric
+        return torch_geometric
+    return None
+
+
+def _cpu_threads() -> int:
+    """Host threads for the CPU arm: the physical cores (half the logical CPUs), also under torchrun -- which
+    exports OMP_NUM_THREADS=1 to every rank and would otherwise cut the CPU arm to one thread at N > 1."""
+    n = max(1, (os.cpu_count() or 2) // 2)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def _reference_step_fn(args):
+    """(step, kind, how): one GCNConv(F, F, cached=True) forward+backward on the bounded CPU sample -- through the
+    reference's own GCNConv when baseline/_ref is installed, else through the restated ATen call sequence."""
     N, E, F = args.cpu_nodes, args.cpu_edges, args.feat
+    torch.manual_seed(0)
     ei = synth_graph(N, E, 1, "cpu")
     x = torch.randn(N, F, requires_grad=True)
+    gout = torch.randn(N, F)
+    tg = _import_reference()
+    if tg is not None:
+        conv = tg.nn.GCNConv(F, F, cached=True)
+
+        def step():
+            x.grad = None
+            conv.zero_grad(set_to_none=True)
+            conv(x, ei).backward(gout)
+        return step, "reference", f"torch_geometric {tg.__version__} GCNConv (baseline/_ref, unmodified), default [2,E] tensor path"
+    from oracle import ref_aten
     weight = torch.nn.Parameter(torch.randn(F, F) / F ** 0.5)
     bias = torch.nn.Parameter(torch.zeros(F))
     ei2, w2 = ref_aten.gcn_norm(ei, None, N)                          # cached=True: outside the loop
-    gout = torch.randn(N, F)
 
     def step():
         x.grad = weight.grad = bias.grad = None
-        out = ref_aten.gcn_conv_forward(x, ei2, w2, weight, bias)
-        out.backward(gout)
+        ref_aten.gcn_conv_forward(x, ei2, w2, weight, bias).backward(gout)
+    return step, "port", "oracle/ref_aten.py (the reference's ATen call sequence; baseline/_ref not installed)"
 
-    for _ in range(max(args.warmup, 1) if args.warmup < 2 else 2):
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path, timed on the host cores on a bounded
+    sample of the workload, exactly --warmup W untimed and --steps K timed steps.  Rank 0 only under torchrun."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = _cpu_threads()
+    step, kind, how = _reference_step_fn(args)
+    N, E, F = args.cpu_nodes, args.cpu_edges, args.feat
+    for _ in range(args.warmup):
         step()
-    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(args.steps):
         step()
-    dt = (time.perf_counter() - t0) / steps
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = E / dt
-    cores = torch.get_num_threads()
-    sample = f"GCNConv({F},{F}) fwd+bwd, N={N}, E={E} power-law, fp32, COO gather->mul->scatter_add_ (reference default path), {steps} steps"
+    sample = (f"{how}; bounded sample of the workload: N={N}, E={E} (same generator), F={F}, fp32, "
+              f"{args.steps} steps, {cores} torch threads of {os.cpu_count()} host CPUs")
     emit({
         "impl": "reference", "metric": "edges/sec (GCNConv fwd+bwd)", "value": value, "unit": "edges/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": sample, "host_cpus": os.cpu_count(), "torch_threads": cores},
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
 
 def cpu_baseline_quick(args):
     """Bounded CPU sample for the `cpu_baseline` object of the main line (rank 0, N=1 only)."""
-    from oracle import ref_aten
+    cores = _cpu_threads()
+    step, kind, how = _reference_step_fn(args)
     N, E, F = args.cpu_nodes, args.cpu_edges, args.feat
-    ei = synth_graph(N, E, 1, "cpu")
-    x = torch.randn(N, F, requires_grad=True)
-    weight = torch.nn.Parameter(torch.randn(F, F) / F ** 0.5)
-    bias = torch.nn.Parameter(torch.zeros(F))
-    ei2, w2 = ref_aten.gcn_norm(ei, None, N)
-    gout = torch.randn(N, F)
-
-    def step():
-        x.grad = weight.grad = bias.grad = None
-        ref_aten.gcn_conv_forward(x, ei2, w2, weight, bias).backward(gout)
-
     step()
     t0 = time.perf_counter()
     n = 0
@@ -201,10 +260,83 @@ def cpu_baseline_quick(args):
         step()
         n += 1
     dt = (time.perf_counter() - t0) / n
-    cores = torch.get_num_threads()
-    return {"value": E / dt, "unit": "edges/s", "cores": cores, "kind": "port",
-            "sample": f"oracle/ref_aten.py GCNConv({F},{F}) fwd+bwd on N={N}, E={E} (same generator), {n} steps, "
+    return {"value": E / dt, "unit": "edges/s", "cores": cores, "kind": kind,
+            "sample": f"{how}; GCNConv({F},{F}) fwd+bwd on N={N}, E={E} (same generator), {n} steps, "
                       f"{cores} torch threads of {os.cpu_count()} host CPUs"}
+
+
+# --------------------------------------------------------------------------- parity at the benchmarked size
+def run_parity(args, conv, fwd, step, ei, x, gout, rank, world, dev):
+    """`parity_check` of the JSON line.  (1) The timed step's out / grad_x / grad_W / grad_b on a seeded sample of
+    destination and source rows (hubs, rows with 0 / 1 / 2 edges, random rows) against the CPU oracle restricted to
+    those rows (oracle/sampled.py), at 1e-5 * sum|terms|.  (2) N > 1: additionally the sharded engine against the
+    unsharded engine on a graph small enough for one GPU, through the very same code path the timed loop used."""
+    import torch.distributed as dist
+
+    from oracle import sampled
+    N = args.nodes
+    out = step()
+    gw, gb = conv.lin.weight.grad, conv.bias.grad
+    res = sampled.gcn_check(ei, rank * N, N, x, conv.lin.weight, conv.bias, gout, out, x.grad, gw, gb,
+                            n_rows=args.parity_rows, seed=17, group=dist.group.WORLD if world > 1 else None)
+    del out
+    if world > 1:
+        res["sharded_vs_unsharded"] = shard_vs_unsharded(args, conv, rank, world, dev)
+        res["ok"] = bool(res["ok"] and res["sharded_vs_unsharded"]["ok"])
+    return res
+
+
+def shard_vs_unsharded(args, conv, rank, world, dev, n_small=100_000, e_small=1_000_000):
+    """Every rank builds the WHOLE small graph (all ranks' seeded edge lists), runs the single-GPU engine on it, and
+    compares its own rows with what the sharded path (same builder, same kernels, same barriers as the timed loop)
+    produces; grad_W / grad_b after the all-reduce."""
+    import torch.distributed as dist
+
+    from pytorch_geometric_b200 import utils as U
+    F = args.feat
+    eis = [synth_graph(n_small, e_small, 1000 + q, dev, lo=q * n_small, total_nodes=world * n_small, p_local=args.p_local)
+           for q in range(world)]
+    xs = [torch.randn(n_small, F, device=dev, generator=torch.Generator(device=dev).manual_seed(2000 + q)) for q in range(world)]
+    gs = [torch.randn(n_small, F, device=dev, generator=torch.Generator(device=dev).manual_seed(3000 + q)) for q in range(world)]
+    x_full = torch.cat(xs).requires_grad_()
+    graph = U.gcn_norm_graph(torch.cat(eis, dim=1), None, world * n_small)
+    conv.zero_grad(set_to_none=True)
+    ref = conv(x_full, graph)
+    ref.backward(torch.cat(gs))
+    ref_gw, ref_gb = conv.lin.weight.grad.clone(), conv.bias.grad.clone()
+    lo = rank * n_small
+    ref_out, ref_gx = ref.detach()[lo:lo + n_small].clone(), x_full.grad[lo:lo + n_small].clone()
+    del ref, x_full, graph
+    conv.zero_grad(set_to_none=True)
+    xl = xs[rank].clone().requires_grad_()
+    if args.dist == "p2p":
+        from pytorch_geometric_b200 import dist_p2p
+        shard = dist_p2p.PeerShardedGCNGraph.build(eis[rank], lo, n_small, world * n_small, F, dist.group.WORLD)
+        shard.gout.copy_(gs[rank])
+        for _ in range(2):                                   # twice: the second pass exercises the reuse barriers
+            xl.grad = None
+            conv.zero_grad(set_to_none=True)
+            out = dist_p2p.peer_sharded_gcn_conv(conv, xl, shard)
+            out.backward(shard.gout)
+    else:
+        from pytorch_geometric_b200 import dist as pdist
+        shard = pdist.ShardedGCNGraph.build(eis[rank], lo, n_small, world * n_small, dist.group.WORLD)
+        out = pdist.sharded_gcn_conv(conv, xl, shard)
+        out.backward(gs[rank])
+    gw, gb = conv.lin.weight.grad.clone(), conv.bias.grad.clone()
+    dist.all_reduce(gw)
+    dist.all_reduce(gb)
+
+    def rel(a, b):                                            # relative to the row's magnitude (sum of |terms| proxy)
+        scale = b.abs().amax(dim=-1, keepdim=True).clamp(min=1e-20) if b.dim() > 1 else b.abs().max().clamp(min=1e-20)
+        return float(((a - b).abs() / scale).max())
+
+    per = {"out": rel(out.detach(), ref_out), "grad_x": rel(xl.grad, ref_gx), "grad_W": rel(gw, ref_gw), "grad_b": rel(gb, ref_gb)}
+    t = torch.tensor([max(per.values())], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    conv.zero_grad(set_to_none=True)
+    return {"nodes": world * n_small, "edges": world * e_small, "p_local": args.p_local, "path": args.dist,
+            "max_rel": float(t.item()), "tol": 2e-5, "ok": bool(t.item() <= 2e-5), "per_quantity_rank0": per}
 
 
 # --------------------------------------------------------------------------- the B200 arm
@@ -245,7 +377,6 @@ def run_b200(args):
     if world == 1:
         ei = synth_graph(N, E, 1, dev)
         graph = U.gcn_norm_graph(ei, None, N)
-        del ei
         graph.build_transpose()
         halo = None
         E_prime = graph.num_edges
@@ -267,16 +398,16 @@ def run_b200(args):
             from pytorch_geometric_b200 import dist as pdist
             shard = pdist.ShardedGCNGraph.build(ei, rank * N, N, world * N, dist.group.WORLD)
             fwd = lambda xx: pdist.sharded_gcn_conv(conv, xx, shard)             # noqa: E731
-        del ei
         E_prime = shard.num_edges
         graph = shard.graph
     torch.cuda.synchronize()
 
-    x = torch.randn(N, F, device=dev).requires_grad_()
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    x = torch.randn(N, F, device=dev, generator=gen).requires_grad_()
     if world > 1 and args.dist == "p2p":
-        gout = shard.gout.normal_()                                   # upstream gradient produced in the symmetric buffer
+        gout = shard.gout.normal_(generator=gen)                      # upstream gradient produced in the symmetric buffer
     else:
-        gout = torch.randn(N, F, device=dev)
+        gout = torch.randn(N, F, device=dev, generator=gen)
 
     def step():
         x.grad = None
@@ -323,7 +454,9 @@ def run_b200(args):
 
     # ---- end to end through the public API with HOST buffers (N=1 path; per rank for N>1)
     e2e = None
+    numa_node = None
     if not args.no_e2e:
+        numa_node = bind_to_gpu_numa_node(local_rank)                         # before the pinned buffer is first touched
         x_host = torch.empty(N, F, dtype=torch.float32, pin_memory=True)
         x_host.normal_()
         # Input prefetch, as a training loop with a pinned-memory loader does it: two device buffers,
@@ -384,23 +517,45 @@ def run_b200(args):
         e2e = {"value": world * E / (ems / n_e2e * 1e-3), "unit": "edges/s",
                "h2d_bytes_per_step": world * N * F * 4, "d2h_bytes_per_step": world * (F * F + F + 1) * 4,
                "ms_per_step": ems / n_e2e, "steps": n_e2e,
+               "host_link_gbs_per_gpu": N * F * 4 / (ems / n_e2e * 1e-3) / 1e9, "numa_node_of_pinned_buffer": numa_node,
                "what": "pinned-host x -> H2D (prefetched one step ahead on a copy stream, double-buffered) -> "
                        "GCNConv fwd+bwd -> D2H of grad_W, grad_b and the loss scalar, every step; "
                        "bound by the 10.24 GB/step host link"}
         del x_host, x_bufs
 
+    # ---- parity at the benchmarked size: one more step, then a seeded row sample against the CPU oracle
+    parity = None
+    if not args.no_parity:
+        parity = run_parity(args, conv, fwd, step, ei, x, gout, rank, world, dev)
+    del ei
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         bytes_pass = pass_bytes(E_prime, N, F)
-        agg = kern.get("spmm_csr", {"ms_total": 0.0, "calls": 0})
+        agg = kern.get("spmm_csr", {"ms_total": 0.0, "calls": 0, "ms_each": []})
         avg_ms = agg["ms_total"] / max(agg["calls"], 1)
         achieved = bytes_pass / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        traffic = traffic_bytes(args) if world == 1 else None
+        # launches alternate forward (destination-sorted CSR) / backward (source-sorted CSR) inside a step
+        by_pass = {}
+        each = agg.get("ms_each", [])
+        for name, sl in (("fwd", each[0::2]), ("bwd", each[1::2])):
+            if sl:
+                m_ = sum(sl) / len(sl)
+                a_ = bytes_pass / (m_ * 1e-3) / 1e9
+                t_ = traffic.get(name) if isinstance(traffic, dict) else None
+                by_pass[name] = {"avg_launch_ms": m_, "achieved": a_, "frac": a_ / peak, "traffic": t_,
+                                 "frac_on_traffic": (t_ / (m_ * 1e-3) / 1e9 / peak) if t_ else None}
         roofline = {"bound": "hbm", "kernel": "csr_reduce_kernel (b200mp_spmm_csr), fwd on CSR + bwd on transposed CSR",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_pass,
                     "avg_launch_ms": avg_ms, "launches_timed": agg["calls"],
                     "share_of_step": agg["ms_total"] / ms if ms > 0 else None,
-                    "traffic": traffic_bytes(args), "frac_of_nominal_8TBs": achieved / 8000.0}
+                    "traffic": (traffic.get("mean") if isinstance(traffic, dict) else traffic),
+                    "traffic_source": ("profiles/traffic.json (ncu --set full capture of this command at this shape, "
+                                       "dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else
+                                       "null: no committed ncu capture for this shape / rank count"),
+                    "by_pass": by_pass, "frac_of_nominal_8TBs": achieved / 8000.0}
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline_quick(args)
@@ -409,9 +564,8 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"GCNConv({F},{F}) fwd+bwd, power-law synthetic graph, N={N} nodes and E={E} edges per GPU"
-                                   f" (E'={E_prime} with self loops), fp32, int32 CSR, graph cached (cached=True)",
-                       "nodes_per_gpu": N, "edges_per_gpu": E, "feat": F, "layers": 1,
+            "config": workload_config(args, world),
+            "engine": {"edges_with_self_loops": E_prime, "index_dtype": "int32",
                        "l2_policy": "inputs (x, grad, CSR > 10 GB) are far larger than the 126 MB L2; no explicit flush",
                        "parallelism": "single GPU" if world == 1 else (
                            f"node-range sharding x{world}, p_local={args.p_local}, " +
@@ -422,8 +576,8 @@ def run_b200(args):
                        "long_rows": graph.plan.n_long, "chunks": graph.plan.n_chunks,
                        "spmm_impl": {0: "default (register-staged lane-group kernel, csrc/csr_reduce.cuh)", 1: "lane-group kernel",
                                      2: "persistent TMA-fed variant (csrc/csr_tma.cuh)"}[args.spmm_impl]},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "kernels": kern, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity_check": parity, "gpu_launches": launches,
+            "kernels": {k: {"ms_total": v["ms_total"], "calls": v["calls"]} for k, v in kern.items()}, "clocks": clocks,
         }
         emit(line)
     if world > 1:
@@ -469,6 +623,8 @@ def main():
                     help="1 = the GEMM kernel splits W tiles itself (one L2 read of W per tile), 0 = pre-split W_hi / W_lo")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check after the timed loop")
+    ap.add_argument("--parity-rows", type=int, default=4096)
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()

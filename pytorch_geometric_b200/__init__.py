@@ -10,5 +10,6 @@ from . import ops, utils  # noqa: F401
 from .functional import aggregate, scatter_coo, segment, softmax_csr  # noqa: F401
 from .graph import CSRGraph  # noqa: F401
 from ._lib import B200MPError, header_symbols, lib  # noqa: F401
+from ._debug import debug, set_debug  # noqa: F401
 
 __version__ = "0.1.0"

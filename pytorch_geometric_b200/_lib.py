@@ -81,12 +81,11 @@ def lib() -> ctypes.CDLL:
         if _build.needs_build():
             try:
                 path = _build.build()
-            except Exception as exc:  # no silent fallback
-                if not os.path.exists(_build.LIB):
-                    raise RuntimeError(
-                        "pytorch_geometric_b200: libb200mp.so is missing and could not be built "
-                        f"({exc}); there is no CPU / eager fallback.") from exc
-                path = _build.LIB
+            except Exception as exc:  # no silent fallback, and no stale library either (its ABI may not match _SIGS)
+                state = "is missing" if not os.path.exists(_build.LIB) else "is stale (sources changed since it was built)"
+                raise RuntimeError(
+                    f"pytorch_geometric_b200: libb200mp.so {state} and could not be rebuilt ({exc}); "
+                    "there is no CPU / eager fallback.") from exc
         l = ctypes.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(l, name)

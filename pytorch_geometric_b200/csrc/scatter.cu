@@ -37,12 +37,13 @@ __global__ void fill_f32_kernel(float* p, int64_t n, float v) {
 template <typename I>
 __global__ void scatter_add_v4_kernel(const float* __restrict__ src, const I* __restrict__ index,
                                       float* __restrict__ out, float* __restrict__ count, int64_t n_src,
-                                      int n_vec) {
+                                      int n_vec, int64_t n_rows) {
     const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t e = t / n_vec;
     const int v = static_cast<int>(t - e * n_vec);
     if (e >= n_src) return;
     const int64_t d = index[e];
+    if (static_cast<uint64_t>(d) >= static_cast<uint64_t>(n_rows)) return;   // out-of-range rows are dropped, never written
     const float4 s = __ldcs(reinterpret_cast<const float4*>(src) + e * n_vec + v);
     red_add_v4(out + (d * n_vec + v) * 4, s.x, s.y, s.z, s.w);
     if (count && v == 0) atomicAdd(count + d, 1.0f);
@@ -51,12 +52,13 @@ __global__ void scatter_add_v4_kernel(const float* __restrict__ src, const I* __
 template <typename I, int RED>
 __global__ void scatter_scalar_kernel(const float* __restrict__ src, const I* __restrict__ index,
                                       float* __restrict__ out, float* __restrict__ count, int64_t n_src,
-                                      int64_t feat) {
+                                      int64_t feat, int64_t n_rows) {
     const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t e = t / feat;
     const int64_t f = t - e * feat;
     if (e >= n_src) return;
     const int64_t d = index[e];
+    if (static_cast<uint64_t>(d) >= static_cast<uint64_t>(n_rows)) return;
     const float s = src[t];
     float* o = out + d * feat + f;
     if (RED == B200MP_SUM) atomicAdd(o, s);
@@ -140,15 +142,15 @@ int scatter_typed(const float* src, const void* index_, float* out, float* count
         const bool v4 = (reduce == B200MP_SUM || reduce == B200MP_MEAN) && feat % 4 == 0 && aligned16(src) && aligned16(out);
         if (v4) {
             const int n_vec = static_cast<int>(feat / 4);
-            scatter_add_v4_kernel<I><<<blocks_for(n_src * n_vec), kT, 0, s>>>(src, index, out, cnt, n_src, n_vec);
+            scatter_add_v4_kernel<I><<<blocks_for(n_src * n_vec), kT, 0, s>>>(src, index, out, cnt, n_src, n_vec, n_rows);
         } else if (reduce == B200MP_SUM || reduce == B200MP_MEAN) {
-            scatter_scalar_kernel<I, B200MP_SUM><<<blocks_for(n_src * feat), kT, 0, s>>>(src, index, out, cnt, n_src, feat);
+            scatter_scalar_kernel<I, B200MP_SUM><<<blocks_for(n_src * feat), kT, 0, s>>>(src, index, out, cnt, n_src, feat, n_rows);
         } else if (reduce == B200MP_MAX) {
-            scatter_scalar_kernel<I, B200MP_MAX><<<blocks_for(n_src * feat), kT, 0, s>>>(src, index, out, cnt, n_src, feat);
+            scatter_scalar_kernel<I, B200MP_MAX><<<blocks_for(n_src * feat), kT, 0, s>>>(src, index, out, cnt, n_src, feat, n_rows);
         } else if (reduce == B200MP_MIN) {
-            scatter_scalar_kernel<I, B200MP_MIN><<<blocks_for(n_src * feat), kT, 0, s>>>(src, index, out, cnt, n_src, feat);
+            scatter_scalar_kernel<I, B200MP_MIN><<<blocks_for(n_src * feat), kT, 0, s>>>(src, index, out, cnt, n_src, feat, n_rows);
         } else {
-            scatter_scalar_kernel<I, B200MP_MUL><<<blocks_for(n_src * feat), kT, 0, s>>>(src, index, out, cnt, n_src, feat);
+            scatter_scalar_kernel<I, B200MP_MUL><<<blocks_for(n_src * feat), kT, 0, s>>>(src, index, out, cnt, n_src, feat, n_rows);
         }
         B200MP_LAUNCH_CHECK();
     }
@@ -202,11 +204,11 @@ extern "C" int b200mp_index_add_rows(const float* src, const void* index, float*
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool v4 = feat % 4 == 0 && aligned16(src) && aligned16(out);
     if (idx_dtype == B200MP_I32) {
-        if (v4) scatter_add_v4_kernel<int32_t><<<blocks_for(n_src * (feat / 4)), kT, 0, s>>>(src, static_cast<const int32_t*>(index), out, nullptr, n_src, static_cast<int>(feat / 4));
-        else scatter_scalar_kernel<int32_t, B200MP_SUM><<<blocks_for(n_src * feat), kT, 0, s>>>(src, static_cast<const int32_t*>(index), out, nullptr, n_src, feat);
+        if (v4) scatter_add_v4_kernel<int32_t><<<blocks_for(n_src * (feat / 4)), kT, 0, s>>>(src, static_cast<const int32_t*>(index), out, nullptr, n_src, static_cast<int>(feat / 4), INT64_MAX);
+        else scatter_scalar_kernel<int32_t, B200MP_SUM><<<blocks_for(n_src * feat), kT, 0, s>>>(src, static_cast<const int32_t*>(index), out, nullptr, n_src, feat, INT64_MAX);
     } else if (idx_dtype == B200MP_I64) {
-        if (v4) scatter_add_v4_kernel<int64_t><<<blocks_for(n_src * (feat / 4)), kT, 0, s>>>(src, static_cast<const int64_t*>(index), out, nullptr, n_src, static_cast<int>(feat / 4));
-        else scatter_scalar_kernel<int64_t, B200MP_SUM><<<blocks_for(n_src * feat), kT, 0, s>>>(src, static_cast<const int64_t*>(index), out, nullptr, n_src, feat);
+        if (v4) scatter_add_v4_kernel<int64_t><<<blocks_for(n_src * (feat / 4)), kT, 0, s>>>(src, static_cast<const int64_t*>(index), out, nullptr, n_src, static_cast<int>(feat / 4), INT64_MAX);
+        else scatter_scalar_kernel<int64_t, B200MP_SUM><<<blocks_for(n_src * feat), kT, 0, s>>>(src, static_cast<const int64_t*>(index), out, nullptr, n_src, feat, INT64_MAX);
     } else {
         set_error("bad idx_dtype %d", idx_dtype);
         return B200MP_ERR_UNSUPPORTED;

@@ -175,15 +175,14 @@ class ShardedGCNGraph:
         dst_l = dst - lo
         # degrees are sums over incoming edges => local; remote sources' dinv comes by halo exchange
         deg = ops.degree(dst_l, n_local).to(torch.float32)
-        if improved and add_self_loops:
-            deg = deg + 1.0                                    # loop weight 2 instead of 1
+        # `improved` only changes the fill value of the inserted loops, and the reference ignores the fill
+        # value when edge_weight is None (gcn_conv.py:98-104 with loop.py:623-657): unweighted graphs -- the
+        # only kind this builder takes -- get loop weight 1 either way, exactly like utils.gcn_norm_graph.
         dinv = deg.pow(-0.5)
         dinv.masked_fill_(dinv == float("inf"), 0.0)
         dinv_halo = exchange_halo(plan, dinv.view(-1, 1), group).view(-1)
         dinv_cat = torch.cat([dinv, dinv_halo])
         w = ops.gather_rows(dinv_cat.view(-1, 1), src_rel).view(-1) * ops.gather_rows(dinv.view(-1, 1), dst_l).view(-1)
-        if improved and add_self_loops:
-            w = torch.where(src_rel == dst_l, w * 2.0, w)
         is_halo = src_rel >= n_local
         keep = ~is_halo
         g_local = CSRGraph(src_rel[keep], dst_l[keep], n_local, n_local, w[keep])

@@ -150,6 +150,10 @@ class _PeerAggregate(torch.autograd.Function):
         shard.barrier()                          # every rank's x W^T is complete before anyone gathers it
         out = ops.spmm_csr(g.rowptr, g.col, g.val, xw, g.num_dst, "sum", g.plan, bias=bias,
                            peer_ptrs=shard.h_xw.buffer_ptrs_dev, peer_rows=shard.n_local)
+        # every rank has finished reading my x W^T rows before anything may overwrite them: without this a
+        # forward-only loop, or two stacked layers sharing one shard, would let the next _LinearInto write
+        # shard.xw while slower peers are still gathering the previous contents over NVLink
+        shard.barrier()
         return out
 
     @staticmethod
@@ -160,7 +164,7 @@ class _PeerAggregate(torch.autograd.Function):
         if grad_out.data_ptr() != shard.gout.data_ptr():
             shard.gout.copy_(grad_out)           # upstream did not produce the gradient in the symmetric buffer
         grad_sym = shard.gout
-        shard.barrier()                          # all forward gathers done (x W^T may be overwritten), all grads in place
+        shard.barrier()                          # every rank's gradient rows are in place before anyone gathers them
         if ctx.needs_input_grad[0]:
             gx = ops.spmm_csr(g.rowptr, g.col, g.val, grad_sym, g.num_dst, "sum", g.plan,
                               peer_ptrs=shard.h_gout.buffer_ptrs_dev, peer_rows=shard.n_local)

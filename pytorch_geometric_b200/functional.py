@@ -87,7 +87,7 @@ class _Segment(torch.autograd.Function):
     def forward(ctx, src: Tensor, ptr: Tensor, reduce: str):
         ctx.plan = ops.segment_plan(ptr, src.size(0))      # hub segments are cut into chunks (csr_reduce.cuh)
         out = ops.segment_csr(src, ptr, reduce, ctx.plan)
-        ctx.reduce = reduce
+        ctx.reduce, ctx.n_src = reduce, src.size(0)
         ctx.save_for_backward(ptr, src if reduce in ("min", "max") else None, out if reduce in ("min", "max") else None)
         return out
 
@@ -95,7 +95,7 @@ class _Segment(torch.autograd.Function):
     def backward(ctx, grad_out: Tensor):
         ptr, src, out = ctx.saved_tensors
         reduce = ctx.reduce
-        n_src = int(ptr[-1])
+        n_src = ctx.n_src                                   # == ptr[-1], known on the host: no D2H read
         index = ops.ptr2index(ptr, n_src)
         g2 = grad_out.contiguous().view(grad_out.size(0), -1)
         if reduce in ("sum", "add"):

@@ -164,9 +164,9 @@ class GINConv(torch.nn.Module):
         self.nn = nn
         self.initial_eps = eps
         if train_eps:
-            self.eps = torch.nn.Parameter(torch.tensor(float(eps)))
+            self.eps = torch.nn.Parameter(torch.full((1, ), float(eps)))     # shape [1] as gin_conv.py:63-65
         else:
-            self.register_buffer("eps", torch.tensor(float(eps)))
+            self.register_buffer("eps", torch.full((1, ), float(eps)))
 
     def forward(self, x, edge_index: Adj, size=None) -> Tensor:
         if isinstance(x, Tensor):

@@ -49,7 +49,11 @@ class _Profile:
 
     def summary(self) -> dict:
         torch.cuda.synchronize()
-        return {k: {"ms_total": sum(a.elapsed_time(b) for a, b in v), "calls": len(v)} for k, v in self.events.items()}
+        out = {}
+        for k, v in self.events.items():
+            each = [a.elapsed_time(b) for a, b in v]
+            out[k] = {"ms_total": sum(each), "calls": len(each), "ms_each": each}
+        return out
 
 
 PROFILE = _Profile()
@@ -286,12 +290,32 @@ SEGMENT_PLAN_MIN_ROWS = 1 << 16   # below this many source rows a hub segment ca
 SEGMENT_CHUNK = 512               # rows per chunk of a long segment (same as graph.DEFAULT_CHUNK)
 
 
+_PLAN_CACHE: "dict" = {}            # id(ptr) -> (weakref(ptr), version, plan or None)
+_PLAN_CACHE_MAX = 32
+
+
 def segment_plan(ptr: Tensor, n_src: int) -> Optional["LongRowPlan"]:
-    """Long-segment plan for segment_csr / multi_aggr_csr (None when the input is too small to need one)."""
+    """Long-segment plan for segment_csr / multi_aggr_csr (None when the input is too small to need one).
+    Counting the long segments needs one device->host read, so the plan is cached per `ptr` tensor OBJECT
+    (weak reference + version counter): a layer that hands over the same ptr every step -- an EdgeIndex's
+    cached indptr, a loader's batch ptr -- pays that read once and enqueues asynchronously afterwards."""
     if n_src < SEGMENT_PLAN_MIN_ROWS:
         return None
+    import weakref
+    key = id(ptr)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None and hit[0]() is ptr and hit[1] == ptr._version:
+        return hit[2]
     plan = LongRowPlan(ptr, SEGMENT_CHUNK)
-    return plan if plan.n_long else None
+    plan = plan if plan.n_long else None
+    if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+        for k in [k for k, v in _PLAN_CACHE.items() if v[0]() is None] or list(_PLAN_CACHE)[:1]:
+            _PLAN_CACHE.pop(k, None)
+    try:
+        _PLAN_CACHE[key] = (weakref.ref(ptr), ptr._version, plan)
+    except TypeError:
+        pass
+    return plan
 
 
 def segment_csr(src: Tensor, ptr: Tensor, reduce: str = "sum", plan: Optional["LongRowPlan"] = None) -> Tensor:

@@ -33,3 +33,24 @@ def assert_close(a, b, rtol=1e-5, atol=1e-6, msg=""):
     tol = atol + rtol * np.abs(b)
     bad = err > tol
     assert not bad.any(), f"{msg} max err {err.max():.3e} at {np.argwhere(bad)[:5].tolist()}"
+
+
+def reference_path():
+    """Where the UNMODIFIED reference package can be imported from: baseline/_ref (installed by
+    baseline/install_ref.sh; travels to the GPU box with the snapshot) or /root/reference (build container only)."""
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(cand, "torch_geometric")):
+            return cand
+    return None
+
+
+@pytest.fixture
+def tg():
+    """The reference package (`import torch_geometric`); the test is skipped where it is not installed."""
+    path = reference_path()
+    if path is None:
+        pytest.skip("the reference package is not installed (baseline/install_ref.sh)")
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import torch_geometric
+    return torch_geometric

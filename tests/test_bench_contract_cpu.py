@@ -22,6 +22,19 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("GCNConv(16,16) fwd+bwd") and d["config"]["n_gpus"] == 1
+
+
+def test_reference_arm_keeps_its_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use the physical cores (round-1 SCALE ratios at
+    N > 1 were inflated by a one-thread reference)."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0", "--cpu-nodes", "2000", "--cpu-edges", "20000", "--feat", "16"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip())
+    assert d["cpu_baseline"]["cores"] == max(1, (os.cpu_count() or 2) // 2) and d["n_gpus"] == 2
 
 
 def test_reference_arm_nonzero_rank_exits_quietly():

@@ -55,6 +55,20 @@ def test_state_dict_layout_matches_reference_layers():
     assert sd["weight"].shape == (3, 8, 16) and sd["root"].shape == (8, 16) and sd["bias"].shape == (16, )
 
 
+def test_state_dict_names_and_shapes_equal_the_reference_layers(tg):
+    """Checkpoints are interchangeable: same keys AND shapes as the reference's five layers (GIN's eps is [1])."""
+    import pytorch_geometric_b200.nn as ours
+    mlp = lambda: torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16))   # noqa: E731
+    cases = [("GCNConv", (8, 16), {}), ("SAGEConv", (8, 16), {}), ("SAGEConv", (8, 16), {"project": True}),
+             ("GATConv", (8, 4), {"heads": 3}), ("GATConv", (8, 4), {"heads": 2, "concat": False, "residual": True}),
+             ("RGCNConv", (8, 16, 3), {}), ("GINConv", (mlp(), ), {"train_eps": True}), ("GINConv", (mlp(), ), {})]
+    for name, args, kw in cases:
+        a = getattr(ours, name)(*args, **kw).state_dict()
+        b = getattr(tg.nn, name)(*args, **kw).state_dict()
+        assert {k: tuple(v.shape) for k, v in a.items()} == {k: tuple(v.shape) for k, v in b.items()}, (name, kw)
+        getattr(ours, name)(*args, **kw).load_state_dict(b)          # a reference checkpoint loads
+
+
 def test_fused_and_multi_aggregation_argument_errors_match_reference_messages():
     # nn/aggr/fused.py:87-110 and multi.py:52-70,101-110: validated before anything touches the device
     from pytorch_geometric_b200.nn import FusedAggregation, MultiAggregation, StdAggregation, aggregation_resolver

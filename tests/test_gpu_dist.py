@@ -62,6 +62,23 @@ def _run_rank(rank, world, port, n_total, n_edges, q, mode="nccl"):
         # sharded
         mine = (ei[1] >= lo) & (ei[1] < lo + n_local)
         xl = x[lo:lo + n_local].to(dev).requires_grad_()
+        if mode == "p2p_stack":
+            # two stacked layers SHARING one shard (one symmetric x W^T buffer), forward-only: the second layer's
+            # dense transform overwrites the buffer the first layer's gather read -- legal only because of the
+            # barrier after the forward gather (no backward with its barriers runs in between)
+            from pytorch_geometric_b200 import dist_p2p
+            conv2 = GCNConv(128, 128).to(dev)
+            with torch.no_grad():
+                conv2.lin.weight.copy_(torch.randn(128, 128, generator=torch.Generator().manual_seed(5)) / 11)
+                conv2.bias.copy_(b)
+                ref2 = conv2(conv(x.to(dev), ei.to(dev)).relu(), ei.to(dev))
+                shard = dist_p2p.PeerShardedGCNGraph.build(ei[:, mine].to(dev), lo, n_local, n_total, 128)
+                for _ in range(4):
+                    h = dist_p2p.peer_sharded_gcn_conv(conv, xl.detach(), shard).relu()
+                    out2 = dist_p2p.peer_sharded_gcn_conv(conv2, h, shard)
+                    torch.testing.assert_close(out2, ref2[lo:lo + n_local], rtol=1e-4, atol=1e-4)
+            q.put((rank, "ok"))
+            return
         if mode == "p2p":
             from pytorch_geometric_b200 import dist_p2p
             shard = dist_p2p.PeerShardedGCNGraph.build(ei[:, mine].to(dev), lo, n_local, n_total, 128)
@@ -116,3 +133,8 @@ def test_sharded_gcn_conv_two_ranks_nccl_equals_unsharded():
 def test_peer_memory_gcn_conv_two_ranks_equals_unsharded():
     """Halo rows gathered over NVLink peer memory inside the kernel (dist_p2p.py)."""
     _launch(2, "p2p")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_peer_memory_two_stacked_layers_share_one_shard_forward_only():
+    _launch(2, "p2p_stack")

@@ -1,25 +1,10 @@
-"""The reference-side binding (pytorch_geometric_b200/install.py), checked in the build container
-where the reference is importable from /root/reference.  On the GPU box the reference does not
-exist, so these tests skip there (nothing at run time may read /root/reference on that box)."""
+"""The reference-side binding (pytorch_geometric_b200/install.py) against the unmodified reference package
+(fixture `tg`: baseline/_ref, else /root/reference in the build container; skipped where neither exists)."""
 import os
 import sys
 
 import pytest
 import torch
-
-REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "torch_geometric")),
-                                reason="the reference is only importable in the build container")
-
-
-@pytest.fixture
-def tg():
-    sys.path.insert(0, REF)
-    try:
-        import torch_geometric
-        yield torch_geometric
-    finally:
-        sys.path.remove(REF)
 
 
 def test_install_rebinds_consumers_and_cpu_falls_through(tg):
