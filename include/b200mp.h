@@ -303,6 +303,51 @@ int b200mp_gat_fused_csr_backward(const void* rowptr, const void* col, const voi
                                   int64_t n_long_rows, int64_t n_chunks, int64_t chunk, float* partials,
                                   int idx_dtype, int val_dtype, void* stream);
 
+/* ------------------------------------------------------------------ fused attention family (csrc/attention.cu)
+ * One kernel skeleton for the three score functions of the reference's attention convolutions, forward and
+ * backward, over the destination-sorted CSR (alpha = softmax over the in-edges of i, utils/_softmax.py:82-88;
+ * out[i,h,:] = sum_e alpha_e,h v[col[e],h,:]):
+ *   mode 0 GAT    s = leaky_relu(s_src[j,h] + s_dst[i,h] (+ s_edge[e,h]))       nn/conv/gat_conv.py:387-409
+ *   mode 1 GATv2  s = sum_c att[h,c] leaky_relu(v[j,h,c] + q[i,h,c])           nn/conv/gatv2_conv.py:358-378
+ *   mode 2 DOT    s = scale <q[i,h,:], k[j,h,:]>                               nn/conv/transformer_conv.py:263-275
+ * v (GAT xh / GATv2 x_l / value rows), k (DOT keys): [n_src, heads*chan] val_dtype with row strides v_stride /
+ * k_stride in ELEMENTS (0 = heads*chan; k and v may be the halves of one [N, 2*H*C] product); q (GATv2 x_r / DOT
+ * queries): [n_rows, heads*chan], stride q_stride; s_src [n_src, heads], s_dst [n_rows, heads], att [heads*chan],
+ * s_edge [n_edges, heads] (CSR order, nullable) fp32.  out [n_rows, heads*chan]; row_max / row_den [n_rows, heads]
+ * fp32 are saved for the backward; alpha_out (nullable) [n_edges, heads] fp32 in CSR order.
+ * Shapes: b200mp_attn_supported(heads, chan, val_dtype) != 0 (rows of whole 16-byte vectors, <= 1 KB, a head =
+ * a power-of-two number of vectors), else B200MP_ERR_UNSUPPORTED.  Hub rows: the long-row plan of
+ * b200mp_csr_plan_* plus part_acc [n_chunks, heads*chan] and part_ms [n_chunks, heads, 2] fp32.
+ *
+ * Backward: destination sweep (softmax backward per edge, grad_q / grad_s_dst / grad_att, and the per-edge scratch
+ * pair [n_edges, heads, 2] fp32 = (alpha, grad_score) in CSR order -- for GAT pair[...,1] is also the gradient of
+ * s_edge) then source sweep on the transposed CSR (t2csr[e] = CSR slot of transposed slot e): grad_v, grad_k (DOT),
+ * grad_s_src (GAT).  Long-row partials: partials [n_chunks, b200mp_attn_backward_partial_width(mode,H,C,0)] and
+ * partials_t [n_chunks_t, ...(mode,H,C,1)] fp32; gatt_part (GATv2) [b200mp_attn_gatt_rows(), heads*chan] fp32. */
+int b200mp_attn_supported(int64_t heads, int64_t chan, int val_dtype);
+int b200mp_attn_csr_forward(int mode, const void* rowptr, const void* col, const void* v, const void* k,
+                            const void* q, const float* s_src, const float* s_dst, const float* att,
+                            const float* s_edge, int64_t v_stride, int64_t k_stride, int64_t q_stride,
+                            void* out, float* row_max, float* row_den, float* alpha_out, int64_t n_rows,
+                            int64_t n_edges, int64_t heads, int64_t chan, float slope, float scale,
+                            const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
+                            int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, int idx_dtype,
+                            int val_dtype, void* stream);
+int64_t b200mp_attn_backward_partial_width(int mode, int64_t heads, int64_t chan, int transposed);
+int64_t b200mp_attn_gatt_rows(void);
+int b200mp_attn_csr_backward(int mode, const void* rowptr, const void* col, const void* rowptr_t,
+                             const void* col_t, const void* t2csr, const void* v, const void* k, const void* q,
+                             const float* s_src, const float* s_dst, const float* att, const float* s_edge,
+                             int64_t v_stride, int64_t k_stride, int64_t q_stride, const float* row_max,
+                             const float* row_den, const void* out, const void* grad_out, float* pair,
+                             void* grad_v, void* grad_k, void* grad_q, float* grad_s_src, float* grad_s_dst,
+                             float* grad_att, float* gatt_part, int64_t n_rows, int64_t n_src, int64_t n_edges,
+                             int64_t heads, int64_t chan, float slope, float scale, const int64_t* long_rows,
+                             const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks, int64_t chunk,
+                             float* partials, const int64_t* long_rows_t, const int64_t* chunk_ptr_t,
+                             int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, int idx_dtype,
+                             int val_dtype, void* stream);
+
 /* ------------------------------------------------------------------ dense transform on tensor cores
  * fp32-accurate 3xTF32 GEMMs (tcgen05 + TMEM + TMA, csrc/gemm_tf32x3.cu) for the layer's
  * Linear (nn/dense/linear.py:121-127: F.linear, run by the reference as strict-fp32 cuBLAS):

@@ -1,0 +1,875 @@
+// attention.cu -- fused edge-softmax attention + weighted aggregation over a destination-sorted CSR, forward
+// and backward, for the three score functions of the reference's attention convolutions:
+//
+//   ATTN_GAT    s_e,h = leaky_relu(a_src[j,h] + a_dst[i,h] (+ a_edge[e,h]))        GATConv     gat_conv.py:387-409
+//   ATTN_GATV2  s_e,h = sum_c att[h,c] leaky_relu(x_l[j,h,c] + x_r[i,h,c])         GATv2Conv   gatv2_conv.py:358-378
+//   ATTN_DOT    s_e,h = scale * <q[i,h,:], k[j,h,:]>                               TransformerConv transformer_conv.py:263-275
+//
+//   alpha = softmax over the in-edges of i (utils/_softmax.py:82-88: exp(s - max) / (sum + 1e-16)),
+//   out[i,h,:] = sum_e alpha_e,h v[j,h,:]        (v = xh / x_l / value rows)
+//
+// The reference runs ~12 kernels and materialises three [E,H,C] tensors; here every pass reads each gathered row
+// once with 128-bit loads and nothing of size E x H x C is ever written.
+//
+// Mapping.  One WARP per work item (a CSR row, or one 512-edge chunk of a hub row -- the plan of csr_reduce.cuh).
+// A row of H*C elements is cut into 16-byte vectors; G = next power of two >= #vectors lanes cover it (VPL = 2
+// vectors per lane above 32 vectors), and the S = 32/G lane groups of the warp walk DIFFERENT EDGES OF THE SAME ROW
+// (edge e0 + u*S + sub), so a warp never idles on the shorter of two unrelated power-law rows; their partial
+// (max, sum, accumulator) states are merged by shuffles at the end with the usual exp(m - M) rescaling.  A head
+// spans LPH = C / (elements per vector) neighbouring lanes; per-head dot products (GATv2 / dot scores, and
+// <grad_out, v> in the backward) are reduced over those lanes with xor-shuffles.
+//
+// Backward, two sweeps, attention recomputed from the saved per-(row, head) max and denominator:
+//   destination sweep (CSR):  D[i,h] = <g[i,h,:], out[i,h,:]> in registers, then per edge
+//        gs_e,h = alpha_e,h (<g[i,h,:], v[j,h,:]> - D[i,h])         (softmax backward)
+//        GAT:   gp = gs * leaky'(pre);  grad_a_dst[i,h] += gp;  pair[e,h] = (alpha, gp)
+//        GATv2: grad_x_r[i,h,c] += gs att[h,c] leaky'(z);  grad_att[h,c] += gs leaky(z);  pair = (alpha, gs)
+//        DOT:   grad_q[i,h,:] += gs scale k[j,h,:];  pair = (alpha, gs scale)
+//   source sweep (transposed CSR, t2csr[e] = CSR slot of transposed slot e):
+//        grad_v[j,h,:] = sum_e alpha_e g[d_e,h,:]  (+ GATv2: gs att leaky'(z));  GAT: grad_a_src[j,h] = sum gp;
+//        DOT: grad_k[j,h,:] = sum_e gs' q[d_e,h,:]
+//   `pair` ([E, H, 2] fp32, CSR order) is the only per-edge scratch: 64 B per edge at H = 8, one 64-byte gather
+//   per edge in the source sweep instead of re-gathering a_dst / max / den and recomputing exp.
+// HBM-bound; algorithmic bytes per edge: forward H*C*s (+ H*C*s for DOT's key row) + H*4 (GAT a_src)
+// + idx; destination sweep the same + H*8 (pair write); source sweep H*C*s (g row) (+ H*C*s for GATv2 x_r / DOT q)
+// + H*8 (pair) + 2 idx.
+#include "csr_reduce.cuh"
+
+namespace b200mp {
+
+enum { ATTN_GAT = 0, ATTN_GATV2 = 1, ATTN_DOT = 2 };
+
+constexpr int kAttnT = 128;   // 4 warps = 4 work items per CTA
+
+struct AttnArgs {
+    const char* v;            // value rows   [n_src, *]  (GAT xh, GATv2 x_l, DOT value)
+    const char* k;            // DOT key rows [n_src, *]
+    const char* q;            // GATv2 x_r / DOT query rows [n_dst, *]
+    const float* s_src;       // GAT a_src [n_src, H]
+    const float* s_dst;       // GAT a_dst [n_dst, H]
+    const float* att;         // GATv2 att [H*C]
+    const float* s_edge;      // GAT optional additive score [E, H] in CSR order (edge_dim)
+    size_t v_stride, k_stride, q_stride;   // row strides in BYTES (k and v may be halves of one [N, 2HC] matrix)
+    int heads, chan, n_vec, lph;
+    float slope, scale;
+};
+
+__device__ __forceinline__ float leaky_f(float v, float slope) { return v > 0.0f ? v : v * slope; }
+
+__device__ __forceinline__ float head_sum(float v, int lph) {
+    for (int o = lph >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// merge (m, s) softmax states: returns the two rescale factors
+__device__ __forceinline__ void merge_ms(float m1, float m2, float& M, float& c1, float& c2) {
+    M = fmaxf(m1, m2);
+    c1 = (m1 == -__builtin_inff()) ? 0.0f : expf(m1 - M);
+    c2 = (m2 == -__builtin_inff()) ? 0.0f : expf(m2 - M);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <typename T, typename I, int G, int VPL, int MODE>
+__global__ void __launch_bounds__(kAttnT)
+attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArgs a, T* __restrict__ out,
+                float* __restrict__ row_max, float* __restrict__ row_den, int64_t n_rows, LongRowPlan plan,
+                float* __restrict__ part_ms) {
+    constexpr int EPV = ElemTraits<T>::kPerVec;
+    constexpr int S = 32 / G;
+    constexpr int UNR = VPL == 1 ? 4 : 2;
+    const int lane = threadIdx.x & 31;
+    const int lig = lane & (G - 1);
+    const int sub = lane / G;
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    int64_t row, begin, end;
+    bool is_chunk;
+    if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;   // warp-uniform
+
+    int head[VPL];
+    bool valid[VPL];
+    float sd[VPL], m[VPL], s[VPL], acc[VPL][EPV], qv[VPL][EPV], av[VPL][EPV];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int v = lig + k * G;
+        valid[k] = v < a.n_vec;
+        head[k] = valid[k] ? (v * EPV) / a.chan : 0;
+        m[k] = -__builtin_inff();
+        s[k] = 0.0f;
+        sd[k] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) acc[k][i] = qv[k][i] = av[k][i] = 0.0f;
+        if (!valid[k]) continue;
+        if (MODE == ATTN_GAT) sd[k] = __ldg(a.s_dst + row * a.heads + head[k]);
+        if (MODE != ATTN_GAT) ElemTraits<T>::unpack(ldg_row16(a.q + static_cast<size_t>(row) * a.q_stride + static_cast<size_t>(v) * 16), qv[k]);
+        if (MODE == ATTN_GATV2) {
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) av[k][i] = __ldg(a.att + v * EPV + i);
+        }
+    }
+
+    for (int64_t e0 = begin; e0 < end; e0 += S * UNR) {
+        Vec16 vb[UNR][VPL], kb[UNR][VPL];
+        float sc[UNR][VPL];
+        bool ev[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t e = e0 + u * S + sub;
+            ev[u] = e < end;
+            if (ev[u]) {
+                const int64_t c = static_cast<int64_t>(ldg_idx(col + e));
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    if (!valid[k]) continue;
+                    const size_t off = static_cast<size_t>(lig + k * G) * 16;
+                    vb[u][k] = ldg_row16(a.v + static_cast<size_t>(c) * a.v_stride + off);
+                    if (MODE == ATTN_DOT) kb[u][k] = ldg_row16(a.k + static_cast<size_t>(c) * a.k_stride + off);
+                    if (MODE == ATTN_GAT) {
+                        sc[u][k] = __ldg(a.s_src + c * a.heads + head[k]);
+                        if (a.s_edge) sc[u][k] += __ldg(a.s_edge + e * a.heads + head[k]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            float f[VPL][EPV], l[VPL];
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                l[k] = 0.0f;
+                if (ev[u] && valid[k]) {
+                    ElemTraits<T>::unpack(vb[u][k], f[k]);
+                    if (MODE == ATTN_GAT) l[k] = leaky_f(sc[u][k] + sd[k], a.slope);
+                    if (MODE == ATTN_GATV2) {
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i], a.slope), l[k]);
+                    }
+                    if (MODE == ATTN_DOT) {
+                        float kf[EPV];
+                        ElemTraits<T>::unpack(kb[u][k], kf);
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(qv[k][i], kf[i], l[k]);
+                    }
+                }
+            }
+            if (MODE != ATTN_GAT) {
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    l[k] = head_sum(l[k], a.lph);                   // executed by the whole warp
+                    if (MODE == ATTN_DOT) l[k] *= a.scale;
+                }
+            }
+            if (ev[u]) {
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    if (!valid[k]) continue;
+                    const float mn = fmaxf(m[k], l[k]);
+                    const float rs = expf(m[k] - mn);               // 0 on the first edge (m = -inf)
+                    const float p = expf(l[k] - mn);
+                    s[k] = fmaf(s[k], rs, p);
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) acc[k][i] = fmaf(acc[k][i], rs, p * f[k][i]);
+                    m[k] = mn;
+                }
+            }
+        }
+    }
+    // merge the S lane groups (they walked disjoint edges of the same row)
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m[k], o);
+            const float s2 = __shfl_xor_sync(0xffffffffu, s[k], o);
+            float M, c1, c2;
+            merge_ms(m[k], m2, M, c1, c2);
+            s[k] = s[k] * c1 + s2 * c2;
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) {
+                const float a2 = __shfl_xor_sync(0xffffffffu, acc[k][i], o);
+                acc[k][i] = acc[k][i] * c1 + a2 * c2;
+            }
+            m[k] = M;
+        }
+    }
+    if (sub != 0) return;
+    const size_t row_bytes = static_cast<size_t>(a.n_vec) * 16;
+    if (is_chunk) {
+        float* pbase = plan.partials + static_cast<size_t>(item) * a.n_vec * EPV;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            if (!valid[k]) continue;
+            const int v = lig + k * G;
+            float* p = pbase + static_cast<size_t>(v) * EPV;
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) p[i] = acc[k][i];
+            if ((v * EPV) % a.chan == 0) {
+                part_ms[(item * a.heads + head[k]) * 2 + 0] = m[k];
+                part_ms[(item * a.heads + head[k]) * 2 + 1] = s[k];
+            }
+        }
+        return;
+    }
+    char* ob = reinterpret_cast<char*>(out) + static_cast<size_t>(row) * row_bytes;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        if (!valid[k]) continue;
+        const int v = lig + k * G;
+        const float den = s[k] + 1e-16f;                           // _softmax.py:87 "+ 1e-16"
+        float f[EPV];
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) f[i] = (end > begin) ? acc[k][i] / den : 0.0f;
+        stg_stream16(ob + static_cast<size_t>(v) * 16, ElemTraits<T>::pack(f));
+        if ((v * EPV) % a.chan == 0) {
+            row_max[row * a.heads + head[k]] = (end > begin) ? m[k] : 0.0f;
+            row_den[row * a.heads + head[k]] = den;
+        }
+    }
+}
+
+// Merge the chunk states of every hub row: M = max_c m_c; S = sum_c s_c e^{m_c-M}; out = sum_c acc_c e^{m_c-M} / (S + 1e-16)
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_combine_kernel(T* __restrict__ out, float* __restrict__ row_max, float* __restrict__ row_den, int heads, int chan,
+                    LongRowPlan plan, const float* __restrict__ part_ms) {
+    const int64_t j = blockIdx.x;
+    if (j >= plan.n_long) return;
+    const int64_t row = plan.long_rows[j];
+    const int64_t c0 = plan.chunk_ptr[j], c1 = plan.chunk_ptr[j + 1];
+    const int64_t hc = static_cast<int64_t>(heads) * chan;
+    for (int64_t f = threadIdx.x; f < hc; f += blockDim.x) {
+        const int h = static_cast<int>(f / chan);
+        float M = -__builtin_inff();
+        for (int64_t c = c0; c < c1; ++c) M = fmaxf(M, part_ms[(c * heads + h) * 2]);
+        float S = 0.0f, acc = 0.0f;
+        for (int64_t c = c0; c < c1; ++c) {
+            const float sc = expf(part_ms[(c * heads + h) * 2] - M);
+            S = fmaf(part_ms[(c * heads + h) * 2 + 1], sc, S);
+            acc = fmaf(plan.partials[c * hc + f], sc, acc);
+        }
+        const float den = S + 1e-16f;
+        out[row * hc + f] = ElemTraits<T>::from_float(acc / den);
+        if (f % chan == 0) {
+            row_max[row * heads + h] = M;
+            row_den[row * heads + h] = den;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward, destination sweep
+// Also the alpha writer of the forward (ALPHA_ONLY: alpha[e,h] from the saved statistics, nothing else).
+template <typename T, typename I, int G, int VPL, int MODE, bool ALPHA_ONLY>
+__global__ void __launch_bounds__(kAttnT)
+attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArgs a, const float* __restrict__ row_max,
+                    const float* __restrict__ row_den, const T* __restrict__ out, const T* __restrict__ grad_out,
+                    float* __restrict__ pair, float* __restrict__ alpha_out, T* __restrict__ grad_q,
+                    float* __restrict__ grad_s_dst, float* __restrict__ gatt_part, int64_t n_rows, LongRowPlan plan) {
+    constexpr int EPV = ElemTraits<T>::kPerVec;
+    constexpr int S = 32 / G;
+    constexpr int UNR = VPL == 1 ? 4 : 2;
+    const int lane = threadIdx.x & 31;
+    const int lig = lane & (G - 1);
+    const int sub = lane / G;
+    const int64_t n_items = plan.n_chunks + n_rows;
+    const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const size_t row_bytes = static_cast<size_t>(a.n_vec) * 16;
+
+    int head[VPL];
+    bool valid[VPL];
+    float av[VPL][EPV], gatt[VPL][EPV];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int v = lig + k * G;
+        valid[k] = v < a.n_vec;
+        head[k] = valid[k] ? (v * EPV) / a.chan : 0;
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) {
+            gatt[k][i] = 0.0f;
+            av[k][i] = (MODE == ATTN_GATV2 && valid[k]) ? __ldg(a.att + v * EPV + i) : 0.0f;
+        }
+    }
+
+    // GATv2 accumulates grad_att over every edge: grid-stride loop over the items (other modes: one item per warp)
+    for (int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps_total) {
+        int64_t row, begin, end;
+        bool is_chunk;
+        if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) continue;
+
+        float sd[VPL], mrow[VPL], inv_den[VPL], D[VPL], gv[VPL][EPV], qv[VPL][EPV], gq[VPL][EPV], gsd[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            const int v = lig + k * G;
+            sd[k] = mrow[k] = inv_den[k] = D[k] = gsd[k] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) gv[k][i] = qv[k][i] = gq[k][i] = 0.0f;
+            if (!valid[k]) continue;
+            mrow[k] = __ldg(row_max + row * a.heads + head[k]);
+            inv_den[k] = 1.0f / __ldg(row_den + row * a.heads + head[k]);
+            if (MODE == ATTN_GAT) sd[k] = __ldg(a.s_dst + row * a.heads + head[k]);
+            if (MODE != ATTN_GAT) ElemTraits<T>::unpack(ldg_row16(a.q + static_cast<size_t>(row) * a.q_stride + static_cast<size_t>(v) * 16), qv[k]);
+            if (!ALPHA_ONLY) {
+                float of[EPV];
+                ElemTraits<T>::unpack(ldg_row16(reinterpret_cast<const char*>(grad_out) + static_cast<size_t>(row) * row_bytes + static_cast<size_t>(v) * 16), gv[k]);
+                ElemTraits<T>::unpack(ldg_row16(reinterpret_cast<const char*>(out) + static_cast<size_t>(row) * row_bytes + static_cast<size_t>(v) * 16), of);
+#pragma unroll
+                for (int i = 0; i < EPV; ++i) D[k] = fmaf(gv[k][i], of[i], D[k]);
+            }
+        }
+        if (!ALPHA_ONLY) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) D[k] = head_sum(D[k], a.lph);
+        }
+
+        for (int64_t e0 = begin; e0 < end; e0 += S * UNR) {
+            Vec16 vb[UNR][VPL], kb[UNR][VPL];
+            float sc[UNR][VPL];
+            bool ev[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t e = e0 + u * S + sub;
+                ev[u] = e < end;
+                if (ev[u]) {
+                    const int64_t c = static_cast<int64_t>(ldg_idx(col + e));
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        if (!valid[k]) continue;
+                        const size_t off = static_cast<size_t>(lig + k * G) * 16;
+                        if (!ALPHA_ONLY || MODE == ATTN_GATV2) vb[u][k] = ldg_row16(a.v + static_cast<size_t>(c) * a.v_stride + off);
+                        if (MODE == ATTN_DOT) kb[u][k] = ldg_row16(a.k + static_cast<size_t>(c) * a.k_stride + off);
+                        if (MODE == ATTN_GAT) {
+                            sc[u][k] = __ldg(a.s_src + c * a.heads + head[k]);
+                            if (a.s_edge) sc[u][k] += __ldg(a.s_edge + e * a.heads + head[k]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t e = e0 + u * S + sub;
+                float f[VPL][EPV], kf[VPL][EPV], l[VPL], dot[VPL];
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    l[k] = dot[k] = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) f[k][i] = kf[k][i] = 0.0f;
+                    if (ev[u] && valid[k]) {
+                        if (!ALPHA_ONLY || MODE == ATTN_GATV2) ElemTraits<T>::unpack(vb[u][k], f[k]);
+                        if (MODE == ATTN_GAT) l[k] = sc[u][k] + sd[k];                       // pre-activation
+                        if (MODE == ATTN_GATV2) {
+#pragma unroll
+                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i], a.slope), l[k]);
+                        }
+                        if (MODE == ATTN_DOT) {
+                            ElemTraits<T>::unpack(kb[u][k], kf[k]);
+#pragma unroll
+                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(qv[k][i], kf[k][i], l[k]);
+                        }
+                        if (!ALPHA_ONLY) {
+#pragma unroll
+                            for (int i = 0; i < EPV; ++i) dot[k] = fmaf(gv[k][i], f[k][i], dot[k]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    if (MODE != ATTN_GAT) {
+                        l[k] = head_sum(l[k], a.lph);
+                        if (MODE == ATTN_DOT) l[k] *= a.scale;
+                    }
+                    if (!ALPHA_ONLY) dot[k] = head_sum(dot[k], a.lph);
+                }
+                if (!ev[u]) continue;
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    if (!valid[k]) continue;
+                    const float score = MODE == ATTN_GAT ? leaky_f(l[k], a.slope) : l[k];
+                    const float alpha = expf(score - mrow[k]) * inv_den[k];
+                    const bool first = ((lig + k * G) * EPV) % a.chan == 0;
+                    if (ALPHA_ONLY) {
+                        if (first) alpha_out[e * a.heads + head[k]] = alpha;
+                        continue;
+                    }
+                    float gs = alpha * (dot[k] - D[k]);
+                    if (MODE == ATTN_GAT) {
+                        gs *= (l[k] > 0.0f ? 1.0f : a.slope);
+                        if (first) gsd[k] += gs;
+                    }
+                    if (MODE == ATTN_GATV2) {
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) {
+                            const float z = f[k][i] + qv[k][i];
+                            gq[k][i] = fmaf(gs * av[k][i], (z > 0.0f ? 1.0f : a.slope), gq[k][i]);
+                            gatt[k][i] = fmaf(gs, leaky_f(z, a.slope), gatt[k][i]);
+                        }
+                    }
+                    if (MODE == ATTN_DOT) {
+                        gs *= a.scale;
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) gq[k][i] = fmaf(gs, kf[k][i], gq[k][i]);
+                    }
+                    if (first) *reinterpret_cast<float2*>(pair + (e * a.heads + head[k]) * 2) = make_float2(alpha, gs);
+                }
+            }
+        }
+        if (ALPHA_ONLY) continue;
+        // sum the lane groups' per-row partial gradients
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                if (MODE == ATTN_GAT) gsd[k] += __shfl_xor_sync(0xffffffffu, gsd[k], o);
+                if (MODE != ATTN_GAT) {
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) gq[k][i] += __shfl_xor_sync(0xffffffffu, gq[k][i], o);
+                }
+            }
+        }
+        if (sub != 0) continue;
+        if (MODE == ATTN_GAT) {
+            // per-row (or per-chunk) sum of grad_pre; chunk partials are folded by attn_sum_combine_kernel
+            float* dstp = is_chunk ? plan.partials + static_cast<size_t>(item) * a.heads : grad_s_dst + row * a.heads;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k)
+                if (valid[k] && ((lig + k * G) * EPV) % a.chan == 0) dstp[head[k]] = gsd[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                if (!valid[k]) continue;
+                const int v = lig + k * G;
+                if (is_chunk) {
+                    float* p = plan.partials + (static_cast<size_t>(item) * a.n_vec + v) * EPV;
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) p[i] = gq[k][i];
+                } else {
+                    stg_stream16(reinterpret_cast<char*>(grad_q) + static_cast<size_t>(row) * row_bytes + static_cast<size_t>(v) * 16,
+                                 ElemTraits<T>::pack(gq[k]));
+                }
+            }
+        }
+    }
+    if (MODE == ATTN_GATV2 && !ALPHA_ONLY) {
+        // fold grad_att: lane groups by shuffle, warps through shared memory, one partial row per CTA
+        __shared__ float sm[kAttnT / 32][64 * 8];
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1)
+#pragma unroll
+            for (int k = 0; k < VPL; ++k)
+#pragma unroll
+                for (int i = 0; i < EPV; ++i) gatt[k][i] += __shfl_xor_sync(0xffffffffu, gatt[k][i], o);
+        const int w = threadIdx.x >> 5;
+        if (sub == 0) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k)
+                if (valid[k])
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) sm[w][(lig + k * G) * EPV + i] = gatt[k][i];
+        }
+        __syncthreads();
+        const int hc = a.heads * a.chan;
+        for (int f = threadIdx.x; f < hc; f += blockDim.x) {
+            float t = 0.0f;
+            for (int ww = 0; ww < kAttnT / 32; ++ww) t += sm[ww][f];
+            gatt_part[static_cast<size_t>(blockIdx.x) * hc + f] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward, source sweep
+template <typename T, typename I, int G, int VPL, int MODE>
+__global__ void __launch_bounds__(kAttnT)
+attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t, const I* __restrict__ t2csr, AttnArgs a,
+                    const T* __restrict__ grad_out, const float* __restrict__ pair, T* __restrict__ grad_v,
+                    T* __restrict__ grad_k, float* __restrict__ grad_s_src, int64_t n_src, LongRowPlan plan) {
+    constexpr int EPV = ElemTraits<T>::kPerVec;
+    constexpr int S = 32 / G;
+    constexpr int UNR = VPL == 1 ? 4 : 2;
+    const int lane = threadIdx.x & 31;
+    const int lig = lane & (G - 1);
+    const int sub = lane / G;
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    int64_t row, begin, end;
+    bool is_chunk;
+    if (!decode_item(item, rowptr_t, n_src, plan, row, begin, end, is_chunk)) return;
+    const size_t row_bytes = static_cast<size_t>(a.n_vec) * 16;
+    const char* gb = reinterpret_cast<const char*>(grad_out);
+
+    int head[VPL];
+    bool valid[VPL];
+    float accv[VPL][EPV], acck[VPL][EPV], xl[VPL][EPV], av[VPL][EPV], gss[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int v = lig + k * G;
+        valid[k] = v < a.n_vec;
+        head[k] = valid[k] ? (v * EPV) / a.chan : 0;
+        gss[k] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) accv[k][i] = acck[k][i] = xl[k][i] = av[k][i] = 0.0f;
+        if (MODE == ATTN_GATV2 && valid[k]) {
+            ElemTraits<T>::unpack(ldg_row16(a.v + static_cast<size_t>(row) * a.v_stride + static_cast<size_t>(v) * 16), xl[k]);
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) av[k][i] = __ldg(a.att + v * EPV + i);
+        }
+    }
+    for (int64_t e0 = begin; e0 < end; e0 += S * UNR) {
+        Vec16 gbuf[UNR][VPL], qb[UNR][VPL];
+        float2 pr[UNR][VPL];
+        bool ev[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t e = e0 + u * S + sub;
+            ev[u] = e < end;
+            if (ev[u]) {
+                const int64_t d = static_cast<int64_t>(ldg_idx(col_t + e));
+                const int64_t p = static_cast<int64_t>(ldg_idx(t2csr + e));
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    if (!valid[k]) continue;
+                    const size_t off = static_cast<size_t>(lig + k * G) * 16;
+                    gbuf[u][k] = ldg_row16(gb + static_cast<size_t>(d) * row_bytes + off);
+                    if (MODE != ATTN_GAT) qb[u][k] = ldg_row16(a.q + static_cast<size_t>(d) * a.q_stride + off);
+                    pr[u][k] = __ldg(reinterpret_cast<const float2*>(pair) + p * a.heads + head[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (!ev[u]) continue;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                if (!valid[k]) continue;
+                float g[EPV];
+                ElemTraits<T>::unpack(gbuf[u][k], g);
+                const float alpha = pr[u][k].x, gs = pr[u][k].y;
+#pragma unroll
+                for (int i = 0; i < EPV; ++i) accv[k][i] = fmaf(alpha, g[i], accv[k][i]);
+                if (MODE == ATTN_GAT) gss[k] += gs;
+                if (MODE != ATTN_GAT) {
+                    float qf[EPV];
+                    ElemTraits<T>::unpack(qb[u][k], qf);
+                    if (MODE == ATTN_GATV2) {
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) accv[k][i] = fmaf(gs * av[k][i], ((xl[k][i] + qf[i]) > 0.0f ? 1.0f : a.slope), accv[k][i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) acck[k][i] = fmaf(gs, qf[i], acck[k][i]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            if (MODE == ATTN_GAT) gss[k] += __shfl_xor_sync(0xffffffffu, gss[k], o);
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) {
+                accv[k][i] += __shfl_xor_sync(0xffffffffu, accv[k][i], o);
+                if (MODE == ATTN_DOT) acck[k][i] += __shfl_xor_sync(0xffffffffu, acck[k][i], o);
+            }
+        }
+    }
+    if (sub != 0) return;
+    // chunk partial layout per chunk: [H*C (grad_v) | H*C (grad_k, DOT) | H (grad_s_src, GAT)] fp32
+    const size_t hc = static_cast<size_t>(a.n_vec) * EPV;
+    const size_t pw = hc * (MODE == ATTN_DOT ? 2 : 1) + (MODE == ATTN_GAT ? a.heads : 0);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        if (!valid[k]) continue;
+        const int v = lig + k * G;
+        const bool first = (v * EPV) % a.chan == 0;
+        if (is_chunk) {
+            float* p = plan.partials + static_cast<size_t>(item) * pw;
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) p[static_cast<size_t>(v) * EPV + i] = accv[k][i];
+            if (MODE == ATTN_DOT) {
+#pragma unroll
+                for (int i = 0; i < EPV; ++i) p[hc + static_cast<size_t>(v) * EPV + i] = acck[k][i];
+            }
+            if (MODE == ATTN_GAT && first) p[hc + head[k]] = gss[k];
+        } else {
+            stg_stream16(reinterpret_cast<char*>(grad_v) + static_cast<size_t>(row) * a.v_stride + static_cast<size_t>(v) * 16, ElemTraits<T>::pack(accv[k]));
+            if (MODE == ATTN_DOT)
+                stg_stream16(reinterpret_cast<char*>(grad_k) + static_cast<size_t>(row) * a.k_stride + static_cast<size_t>(v) * 16, ElemTraits<T>::pack(acck[k]));
+            if (MODE == ATTN_GAT && first) grad_s_src[row * a.heads + head[k]] = gss[k];
+        }
+    }
+}
+
+// Fold fp32 chunk partials [n_chunks, width] of every long row, in chunk order, into up to two typed row outputs
+// (w0 / w1 elements at row strides s0 / s1 BYTES) and one fp32 output (wf floats per row).
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_sum_combine_kernel(LongRowPlan plan, int64_t width, T* __restrict__ o0, int64_t w0, size_t s0, T* __restrict__ o1,
+                        int64_t w1, size_t s1, float* __restrict__ of, int64_t wf) {
+    const int64_t j = blockIdx.x;
+    if (j >= plan.n_long) return;
+    const int64_t row = plan.long_rows[j];
+    const int64_t c0 = plan.chunk_ptr[j], c1 = plan.chunk_ptr[j + 1];
+    for (int64_t f = threadIdx.x; f < width; f += blockDim.x) {
+        float acc = 0.0f;
+        for (int64_t c = c0; c < c1; ++c) acc += plan.partials[c * width + f];
+        if (f < w0) reinterpret_cast<T*>(reinterpret_cast<char*>(o0) + row * s0)[f] = ElemTraits<T>::from_float(acc);
+        else if (f < w0 + w1) reinterpret_cast<T*>(reinterpret_cast<char*>(o1) + row * s1)[f - w0] = ElemTraits<T>::from_float(acc);
+        else of[row * wf + (f - w0 - w1)] = acc;
+    }
+}
+
+// grad_att = sum over the per-CTA partial rows (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+attn_fold_rows_kernel(const float* __restrict__ part, int64_t n_part, int64_t width, float* __restrict__ out) {
+    const int64_t f = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= width) return;
+    float acc = 0.0f;
+    for (int64_t p = 0; p < n_part; ++p) acc += part[p * width + f];
+    out[f] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+inline bool pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <typename T>
+bool attn_vec_ok(int64_t heads, int64_t chan, const AttnArgs& a, const void* out) {
+    constexpr int EPV = ElemTraits<T>::kPerVec;
+    const size_t row_bytes = static_cast<size_t>(heads * chan) * sizeof(T);
+    if (row_bytes % 16 != 0 || chan % EPV != 0 || row_bytes / 16 > 64) return false;
+    const int64_t lph = chan / EPV;
+    if (!pow2(lph) || lph > 32) return false;
+    if (!aligned16(a.v) || a.v_stride % 16 != 0 || (out && !aligned16(out))) return false;
+    if (a.k && (!aligned16(a.k) || a.k_stride % 16 != 0)) return false;
+    if (a.q && (!aligned16(a.q) || a.q_stride % 16 != 0)) return false;
+    return true;
+}
+
+#define ATTN_BY_SHAPE(LAUNCH)                      \
+    do {                                           \
+        if (n_vec <= 1) { LAUNCH(1, 1); }          \
+        else if (n_vec <= 2) { LAUNCH(2, 1); }     \
+        else if (n_vec <= 4) { LAUNCH(4, 1); }     \
+        else if (n_vec <= 8) { LAUNCH(8, 1); }     \
+        else if (n_vec <= 16) { LAUNCH(16, 1); }   \
+        else if (n_vec <= 32) { LAUNCH(32, 1); }   \
+        else { LAUNCH(32, 2); }                    \
+    } while (0)
+
+template <typename T, typename I, int MODE>
+int attn_forward_typed(const void* rowptr_, const void* col_, AttnArgs a, void* out_, float* row_max, float* row_den,
+                       float* alpha_out, int64_t n_rows, int64_t n_edges, LongRowPlan plan, float* part_ms, cudaStream_t s) {
+    const I* rowptr = static_cast<const I*>(rowptr_);
+    const I* col = static_cast<const I*>(col_);
+    T* out = static_cast<T*>(out_);
+    const int n_vec = a.n_vec;
+    const int64_t items = plan.n_chunks + n_rows;
+    const unsigned blocks = static_cast<unsigned>(ceil_div(items, kAttnT / 32));
+#define ATTN_FWD(G_, V_) attn_fwd_kernel<T, I, G_, V_, MODE><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, out, row_max, row_den, n_rows, plan, part_ms)
+    ATTN_BY_SHAPE(ATTN_FWD);
+#undef ATTN_FWD
+    B200MP_LAUNCH_CHECK();
+    if (plan.n_long > 0) {
+        attn_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), 256, 0, s>>>(out, row_max, row_den, a.heads, a.chan, plan, part_ms);
+        B200MP_LAUNCH_CHECK();
+    }
+    if (alpha_out && n_edges > 0) {
+        LongRowPlan np = plan;
+        np.partials = nullptr;
+#define ATTN_ALPHA(G_, V_) attn_bwd_dst_kernel<T, I, G_, V_, MODE, true><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, row_max, row_den, nullptr, nullptr, nullptr, alpha_out, nullptr, nullptr, nullptr, n_rows, np)
+        ATTN_BY_SHAPE(ATTN_ALPHA);
+#undef ATTN_ALPHA
+        B200MP_LAUNCH_CHECK();
+    }
+    return B200MP_OK;
+}
+
+template <typename T, typename I, int MODE>
+int attn_backward_typed(const void* rowptr_, const void* col_, const void* rowptr_t_, const void* col_t_, const void* t2csr_,
+                        AttnArgs a, const float* row_max, const float* row_den, const void* out, const void* grad_out,
+                        float* pair, void* grad_v, void* grad_k, void* grad_q, float* grad_s_src, float* grad_s_dst,
+                        float* grad_att, float* gatt_part, int64_t gatt_rows, int64_t n_rows, int64_t n_src, LongRowPlan plan,
+                        LongRowPlan plan_t, cudaStream_t s) {
+    constexpr int EPV = ElemTraits<T>::kPerVec;
+    const I* rowptr = static_cast<const I*>(rowptr_);
+    const I* col = static_cast<const I*>(col_);
+    const int n_vec = a.n_vec;
+    const int64_t hc = static_cast<int64_t>(n_vec) * EPV;
+    if (n_rows > 0) {
+        const int64_t items = plan.n_chunks + n_rows;
+        unsigned blocks = static_cast<unsigned>(ceil_div(items, kAttnT / 32));
+        if (MODE == ATTN_GATV2 && blocks > static_cast<unsigned>(gatt_rows)) blocks = static_cast<unsigned>(gatt_rows);   // persistent
+#define ATTN_DST(G_, V_) attn_bwd_dst_kernel<T, I, G_, V_, MODE, false><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, row_max, row_den, static_cast<const T*>(out), static_cast<const T*>(grad_out), pair, nullptr, static_cast<T*>(grad_q), grad_s_dst, gatt_part, n_rows, plan)
+        ATTN_BY_SHAPE(ATTN_DST);
+#undef ATTN_DST
+        B200MP_LAUNCH_CHECK();
+        if (plan.n_long > 0) {
+            if (MODE == ATTN_GAT)
+                attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), 256, 0, s>>>(plan, a.heads, nullptr, 0, 0, nullptr, 0, 0, grad_s_dst, a.heads);
+            else
+                attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), 256, 0, s>>>(plan, hc, static_cast<T*>(grad_q), hc, static_cast<size_t>(hc) * sizeof(T), nullptr, 0, 0, nullptr, 0);
+            B200MP_LAUNCH_CHECK();
+        }
+        if (MODE == ATTN_GATV2) {
+            attn_fold_rows_kernel<<<static_cast<unsigned>(ceil_div(hc, 256)), 256, 0, s>>>(gatt_part, blocks, hc, grad_att);
+            B200MP_LAUNCH_CHECK();
+        }
+    }
+    if (n_src > 0) {
+        const int64_t items = plan_t.n_chunks + n_src;
+        const unsigned blocks = static_cast<unsigned>(ceil_div(items, kAttnT / 32));
+#define ATTN_SRC(G_, V_) attn_bwd_src_kernel<T, I, G_, V_, MODE><<<blocks, kAttnT, 0, s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
+        ATTN_BY_SHAPE(ATTN_SRC);
+#undef ATTN_SRC
+        B200MP_LAUNCH_CHECK();
+        if (plan_t.n_long > 0) {
+            const int64_t w1 = MODE == ATTN_DOT ? hc : 0, wf = MODE == ATTN_GAT ? a.heads : 0;
+            attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan_t.n_long), 256, 0, s>>>(
+                plan_t, hc + w1 + wf, static_cast<T*>(grad_v), hc, a.v_stride, static_cast<T*>(grad_k), w1, a.k_stride, grad_s_src, wf);
+            B200MP_LAUNCH_CHECK();
+        }
+    }
+    return B200MP_OK;
+}
+
+}  // namespace b200mp
+
+using namespace b200mp;
+
+namespace {
+
+int fill_args(AttnArgs& a, int mode, const void* v, const void* k, const void* q, const float* s_src, const float* s_dst,
+              const float* att, const float* s_edge, int64_t v_stride, int64_t k_stride, int64_t q_stride, int64_t heads,
+              int64_t chan, float slope, float scale, int val_dtype) {
+    const size_t es = val_dtype == B200MP_BF16 ? 2 : 4;
+    const size_t hc_bytes = static_cast<size_t>(heads * chan) * es;
+    a.v = static_cast<const char*>(v);
+    a.k = static_cast<const char*>(k);
+    a.q = static_cast<const char*>(q);
+    a.s_src = s_src;
+    a.s_dst = s_dst;
+    a.att = att;
+    a.s_edge = s_edge;
+    a.v_stride = v_stride > 0 ? static_cast<size_t>(v_stride) * es : hc_bytes;
+    a.k_stride = k_stride > 0 ? static_cast<size_t>(k_stride) * es : hc_bytes;
+    a.q_stride = q_stride > 0 ? static_cast<size_t>(q_stride) * es : hc_bytes;
+    a.heads = static_cast<int>(heads);
+    a.chan = static_cast<int>(chan);
+    a.n_vec = static_cast<int>(hc_bytes / 16);
+    a.lph = static_cast<int>(chan / (16 / es));
+    a.slope = slope;
+    a.scale = scale;
+    if (mode == ATTN_GAT && !(s_src && s_dst)) return 1;
+    if (mode == ATTN_GATV2 && !(q && att)) return 1;
+    if (mode == ATTN_DOT && !(q && k)) return 1;
+    return 0;
+}
+
+}  // namespace
+
+#define ATTN_DISPATCH(FN, ...)                                                                                           \
+    do {                                                                                                                 \
+        if (val_dtype == B200MP_F32 && idx_dtype == B200MP_I32) {                                                        \
+            if (mode == ATTN_GAT) return FN<float, int32_t, ATTN_GAT>(__VA_ARGS__);                                      \
+            if (mode == ATTN_GATV2) return FN<float, int32_t, ATTN_GATV2>(__VA_ARGS__);                                  \
+            return FN<float, int32_t, ATTN_DOT>(__VA_ARGS__);                                                            \
+        }                                                                                                                \
+        if (val_dtype == B200MP_F32 && idx_dtype == B200MP_I64) {                                                        \
+            if (mode == ATTN_GAT) return FN<float, int64_t, ATTN_GAT>(__VA_ARGS__);                                      \
+            if (mode == ATTN_GATV2) return FN<float, int64_t, ATTN_GATV2>(__VA_ARGS__);                                  \
+            return FN<float, int64_t, ATTN_DOT>(__VA_ARGS__);                                                            \
+        }                                                                                                                \
+        if (val_dtype == B200MP_BF16 && idx_dtype == B200MP_I32) {                                                       \
+            if (mode == ATTN_GAT) return FN<__nv_bfloat16, int32_t, ATTN_GAT>(__VA_ARGS__);                              \
+            if (mode == ATTN_GATV2) return FN<__nv_bfloat16, int32_t, ATTN_GATV2>(__VA_ARGS__);                          \
+            return FN<__nv_bfloat16, int32_t, ATTN_DOT>(__VA_ARGS__);                                                    \
+        }                                                                                                                \
+        if (val_dtype == B200MP_BF16 && idx_dtype == B200MP_I64) {                                                       \
+            if (mode == ATTN_GAT) return FN<__nv_bfloat16, int64_t, ATTN_GAT>(__VA_ARGS__);                              \
+            if (mode == ATTN_GATV2) return FN<__nv_bfloat16, int64_t, ATTN_GATV2>(__VA_ARGS__);                          \
+            return FN<__nv_bfloat16, int64_t, ATTN_DOT>(__VA_ARGS__);                                                    \
+        }                                                                                                                \
+        set_error("attn: unsupported dtype combination val=%d idx=%d", val_dtype, idx_dtype);                            \
+        return B200MP_ERR_UNSUPPORTED;                                                                                   \
+    } while (0)
+
+extern "C" int b200mp_attn_supported(int64_t heads, int64_t chan, int val_dtype) {
+    const int64_t es = val_dtype == B200MP_BF16 ? 2 : 4;
+    const int64_t epv = 16 / es;
+    const int64_t row_bytes = heads * chan * es;
+    if (heads <= 0 || chan <= 0 || row_bytes % 16 != 0 || chan % epv != 0 || row_bytes / 16 > 64) return 0;
+    const int64_t lph = chan / epv;
+    return (lph & (lph - 1)) == 0 && lph <= 32;
+}
+
+extern "C" int b200mp_attn_csr_forward(int mode, const void* rowptr, const void* col, const void* v, const void* k,
+                                       const void* q, const float* s_src, const float* s_dst, const float* att,
+                                       const float* s_edge, int64_t v_stride, int64_t k_stride, int64_t q_stride,
+                                       void* out, float* row_max, float* row_den, float* alpha_out, int64_t n_rows,
+                                       int64_t n_edges, int64_t heads, int64_t chan, float slope, float scale,
+                                       const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
+                                       int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, int idx_dtype,
+                                       int val_dtype, void* stream) {
+    B200MP_CHECK_ARG(mode >= ATTN_GAT && mode <= ATTN_DOT);
+    B200MP_CHECK_ARG(n_rows >= 0 && n_edges >= 0 && heads > 0 && chan > 0);
+    if (n_rows == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(rowptr && out && row_max && row_den && (n_edges == 0 || (col && v)));
+    B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && part_acc && part_ms && chunk > 0));
+    AttnArgs a;
+    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype)) {
+        set_error("attn forward: operands missing for mode %d", mode);
+        return B200MP_ERR_INVALID_ARG;
+    }
+    if (!b200mp_attn_supported(heads, chan, val_dtype) || !aligned16(v) || !aligned16(out) || a.v_stride % 16 || a.k_stride % 16 ||
+        a.q_stride % 16 || (k && !aligned16(k)) || (q && !aligned16(q))) {
+        set_error("attn forward: shape H=%lld C=%lld not on the vector path (rows must be 16-byte vectors, <= 1 KB, C/vector a power of two)",
+                  static_cast<long long>(heads), static_cast<long long>(chan));
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    LongRowPlan plan{long_rows, chunk_ptr, n_long_rows, n_long_rows ? n_chunks : 0, chunk, part_acc};
+    ATTN_DISPATCH(attn_forward_typed, rowptr, col, a, out, row_max, row_den, alpha_out, n_rows, n_edges, plan, part_ms,
+                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int64_t b200mp_attn_backward_partial_width(int mode, int64_t heads, int64_t chan, int transposed) {
+    /* fp32 elements per chunk of the long-row partial buffers (destination sweep / source sweep) */
+    const int64_t hc = heads * chan;
+    if (!transposed) return mode == ATTN_GAT ? heads : hc;
+    return hc * (mode == ATTN_DOT ? 2 : 1) + (mode == ATTN_GAT ? heads : 0);
+}
+
+extern "C" int64_t b200mp_attn_gatt_rows(void) { return static_cast<int64_t>(num_sms()) * 8; }
+
+extern "C" int b200mp_attn_csr_backward(int mode, const void* rowptr, const void* col, const void* rowptr_t, const void* col_t,
+                                        const void* t2csr, const void* v, const void* k, const void* q, const float* s_src,
+                                        const float* s_dst, const float* att, const float* s_edge, int64_t v_stride,
+                                        int64_t k_stride, int64_t q_stride, const float* row_max, const float* row_den,
+                                        const void* out, const void* grad_out, float* pair, void* grad_v, void* grad_k,
+                                        void* grad_q, float* grad_s_src, float* grad_s_dst, float* grad_att,
+                                        float* gatt_part, int64_t n_rows, int64_t n_src, int64_t n_edges, int64_t heads,
+                                        int64_t chan, float slope, float scale, const int64_t* long_rows,
+                                        const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks, int64_t chunk,
+                                        float* partials, const int64_t* long_rows_t, const int64_t* chunk_ptr_t,
+                                        int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, int idx_dtype,
+                                        int val_dtype, void* stream) {
+    B200MP_CHECK_ARG(mode >= ATTN_GAT && mode <= ATTN_DOT);
+    B200MP_CHECK_ARG(n_rows >= 0 && n_src >= 0 && n_edges >= 0 && heads > 0 && chan > 0);
+    B200MP_CHECK_ARG(rowptr && rowptr_t && grad_v && row_max && row_den && out && grad_out);
+    B200MP_CHECK_ARG(n_edges == 0 || (col && col_t && t2csr && pair));
+    B200MP_CHECK_ARG(mode != ATTN_GAT || (grad_s_src && grad_s_dst));
+    B200MP_CHECK_ARG(mode == ATTN_GAT || grad_q);
+    B200MP_CHECK_ARG(mode != ATTN_DOT || grad_k);
+    B200MP_CHECK_ARG(mode != ATTN_GATV2 || (grad_att && gatt_part));
+    B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && partials && chunk > 0));
+    B200MP_CHECK_ARG(n_long_rows_t == 0 || (long_rows_t && chunk_ptr_t && partials_t && chunk > 0));
+    AttnArgs a;
+    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype)) {
+        set_error("attn backward: operands missing for mode %d", mode);
+        return B200MP_ERR_INVALID_ARG;
+    }
+    if (!b200mp_attn_supported(heads, chan, val_dtype) || !aligned16(v) || !aligned16(out) || !aligned16(grad_out) || !aligned16(grad_v) ||
+        a.v_stride % 16 || a.k_stride % 16 || a.q_stride % 16 || heads * chan > 64 * 8) {
+        set_error("attn backward: shape H=%lld C=%lld not on the vector path", static_cast<long long>(heads), static_cast<long long>(chan));
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    LongRowPlan plan{long_rows, chunk_ptr, n_long_rows, n_long_rows ? n_chunks : 0, chunk, partials};
+    LongRowPlan plan_t{long_rows_t, chunk_ptr_t, n_long_rows_t, n_long_rows_t ? n_chunks_t : 0, chunk, partials_t};
+    ATTN_DISPATCH(attn_backward_typed, rowptr, col, rowptr_t, col_t, t2csr, a, row_max, row_den, out, grad_out, pair, grad_v,
+                  grad_k, grad_q, grad_s_src, grad_s_dst, grad_att, gatt_part, b200mp_attn_gatt_rows(), n_rows, n_src, plan, plan_t,
+                  static_cast<cudaStream_t>(stream));
+}

@@ -202,8 +202,130 @@ def gat_attention(graph: CSRGraph, xh: Tensor, a_src: Tensor, a_dst: Tensor, hea
     """out[i,h,:] = sum_e softmax_i(leaky_relu(a_src[j,h] + a_dst[i,h]))_e * xh[j,h,:]
     (GATConv.edge_update + message + aggregate, gat_conv.py:387-409) in one fused sweep.
     xh: [num_src, H*C]; returns out [num_dst, H*C] (and alpha [E, H] in CSR order)."""
+    if ops.attn_supported(heads, chan, xh.dtype) and xh.data_ptr() % 16 == 0:
+        return attention("gat", graph, heads, chan, v=xh, s_src=a_src, s_dst=a_dst, negative_slope=negative_slope,
+                         return_alpha=return_alpha)
+    # head widths off the vector path: the scalar kernels of csrc/gat.cu (no padding copy needed for GAT)
     out, alpha = _GATFused.apply(xh, a_src, a_dst, graph, heads, chan, float(negative_slope), return_alpha)
     return (out, alpha) if return_alpha else out
+
+
+class _AttnFused(torch.autograd.Function):
+    """Fused attention family (csrc/attention.cu): GAT / GATv2 / dot-product scores, edge softmax and the weighted
+    aggregation in one sweep; backward = destination sweep + source sweep with the attention recomputed."""
+
+    @staticmethod
+    def forward(ctx, mode: str, graph: CSRGraph, heads: int, chan: int, slope: float, scale: float, want_alpha: bool,
+                v: Tensor, k: Optional[Tensor], q: Optional[Tensor], s_src: Optional[Tensor], s_dst: Optional[Tensor],
+                att: Optional[Tensor], s_edge: Optional[Tensor], kv: Optional[Tensor]):
+        hc = heads * chan
+        if kv is not None:                                   # keys | values as the two halves of one [N, 2HC] product
+            k, v = kv[:, :hc], kv[:, hc:]
+        f32 = lambda t: None if t is None else t.detach().float().contiguous()   # noqa: E731
+        s_src32, s_dst32, att32 = f32(s_src), f32(s_dst), (None if att is None else f32(att).view(-1))
+        s_edge_csr = None if s_edge is None else graph.to_csr_order_rows(f32(s_edge))
+        if q is not None and q.stride(1) != 1:
+            q = q.contiguous()
+        out, row_max, row_den, alpha = ops.attn_forward(mode, graph.rowptr, graph.col, v, heads, chan, k=k, q=q, s_src=s_src32,
+                                                        s_dst=s_dst32, att=att32, s_edge=s_edge_csr, slope=slope, scale=scale,
+                                                        want_alpha=want_alpha, plan=graph.plan)
+        ctx.mode, ctx.graph, ctx.dims, ctx.fused_kv = mode, graph, (heads, chan, slope, scale), kv is not None
+        ctx.dt = tuple(None if t is None else t.dtype for t in (s_src, s_dst, att, s_edge))
+        ctx.save_for_backward(kv if kv is not None else v, None if kv is not None else k, q, s_src32, s_dst32, att32, s_edge_csr,
+                              row_max, row_den, out)
+        if alpha is None:
+            alpha = out.new_empty(0)
+        ctx.mark_non_differentiable(alpha)
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor, _grad_alpha):
+        v, k, q, s_src, s_dst, att, s_edge, row_max, row_den, out = ctx.saved_tensors
+        graph = ctx.graph
+        heads, chan, slope, scale = ctx.dims
+        hc = heads * chan
+        graph.build_transpose()
+        grad_kv = grad_v = grad_k = None
+        if ctx.fused_kv:
+            kv = v
+            k, v = kv[:, :hc], kv[:, hc:]
+            grad_kv = torch.empty_like(kv)
+            grad_k, grad_v = grad_kv[:, :hc], grad_kv[:, hc:]
+        r = ops.attn_backward(ctx.mode, graph.rowptr, graph.col, graph.rowptr_t, graph.col_t, graph.t2csr, v, heads, chan,
+                              row_max, row_den, out, grad_out, k=k, q=q, s_src=s_src, s_dst=s_dst, att=att, s_edge=s_edge,
+                              slope=slope, scale=scale, plan=graph.plan, plan_t=graph.plan_t, grad_v=grad_v, grad_k=grad_k)
+        cast = lambda t, d: None if (t is None or d is None) else t.to(d)       # noqa: E731
+        g_edge = None
+        if s_edge is not None:
+            g_edge = cast(graph.from_csr_order_rows(r["grad_s_edge"].contiguous()), ctx.dt[3])
+        g_att = None if r["grad_att"] is None else cast(r["grad_att"], ctx.dt[2])
+        return (None, None, None, None, None, None, None,
+                None if ctx.fused_kv else r["grad_v"], None if ctx.fused_kv else r["grad_k"], r["grad_q"],
+                cast(r["grad_s_src"], ctx.dt[0]), cast(r["grad_s_dst"], ctx.dt[1]), g_att, g_edge, grad_kv)
+
+
+def _vector_shape(heads: int, chan: int, dtype: torch.dtype):
+    """(chan_padded, heads_per_group) that put [*, heads*chan] rows on the vector path of csrc/attention.cu:
+    a head is a power-of-two number of 16-byte vectors and a row group is at most 1 KB."""
+    epv = 8 if dtype == torch.bfloat16 else 4
+    vec = -(-chan // epv)
+    lph = 1
+    while lph < vec:
+        lph *= 2
+    if lph > 32:
+        raise NotImplementedError(f"attention heads wider than 512 bytes (C = {chan}) are not on the fused path")
+    chan_p = lph * epv
+    per_group = max(1, 64 // lph)
+    return chan_p, min(heads, per_group)
+
+
+def attention(mode: str, graph: CSRGraph, heads: int, chan: int, *, v: Optional[Tensor] = None, k: Optional[Tensor] = None,
+              q: Optional[Tensor] = None, kv: Optional[Tensor] = None, s_src: Optional[Tensor] = None,
+              s_dst: Optional[Tensor] = None, att: Optional[Tensor] = None, s_edge: Optional[Tensor] = None,
+              negative_slope: float = 0.2, scale: float = 1.0, return_alpha: bool = False):
+    """out[i,h,:] = sum_e softmax_i(score_e,h) v[j,h,:] for mode in {"gat", "gatv2", "dot"} (see csrc/attention.cu).
+    All feature operands are [n, H*C]; `kv` = [n_src, 2*H*C] (keys | values from one fused product) instead of k, v;
+    s_edge [E, H] in the caller's edge order.  Returns out (and alpha [E, H] in CSR order).
+
+    Head widths off the kernel's vector path (C not a power-of-two number of 16-byte vectors, rows above 1 KB) are
+    mapped onto it: channels are zero-padded per head (zeros change neither a score nor a sum) and heads -- which are
+    independent -- are processed in groups; the kernels are the same."""
+    ref = kv if kv is not None else v
+    dtype = ref.dtype
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"attention operands must be float32 or bfloat16, got {dtype}")
+    chan_p, hpg = _vector_shape(heads, chan, dtype)
+    if chan_p == chan and hpg == heads and ops.attn_supported(heads, chan, dtype):
+        out, alpha = _AttnFused.apply(mode, graph, heads, chan, float(negative_slope), float(scale), return_alpha, v, k, q,
+                                      s_src, s_dst, att if att is None else att.reshape(-1), s_edge, kv)
+        return (out, alpha) if return_alpha else out
+    if kv is not None:
+        k, v = kv[:, :heads * chan], kv[:, heads * chan:]
+
+    def group(t, h0, h1, feat: bool):
+        if t is None:
+            return None
+        if not feat:                                        # [n, H] scalars per head
+            return t[:, h0:h1]
+        t3 = t.reshape(t.size(0), heads, chan)[:, h0:h1]
+        if chan_p != chan:
+            t3 = torch.nn.functional.pad(t3, (0, chan_p - chan))
+        return t3.reshape(t.size(0), (h1 - h0) * chan_p).contiguous()
+
+    outs, alphas = [], []
+    for h0 in range(0, heads, hpg):
+        h1 = min(h0 + hpg, heads)
+        a_g = None if att is None else group(att.reshape(1, heads * chan), h0, h1, True).view(-1)
+        o, al = _AttnFused.apply(mode, graph, h1 - h0, chan_p, float(negative_slope), float(scale), return_alpha,
+                                 group(v, h0, h1, True), group(k, h0, h1, True), group(q, h0, h1, True),
+                                 group(s_src, h0, h1, False), group(s_dst, h0, h1, False), a_g, group(s_edge, h0, h1, False),
+                                 None)
+        outs.append(o.view(o.size(0), h1 - h0, chan_p)[:, :, :chan])
+        alphas.append(al)
+    out = torch.cat(outs, dim=1).reshape(outs[0].size(0), heads * chan)
+    if return_alpha:
+        return out, torch.cat(alphas, dim=1)
+    return out
 
 
 class _MultiAggregate(torch.autograd.Function):

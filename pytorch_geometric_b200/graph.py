@@ -101,6 +101,15 @@ class CSRGraph:
             self._inv_perm_t = self._inverse(self.perm_t)
         return ops.permute(per_edge_csc.contiguous(), self._inv_perm_t)
 
+    def to_csr_order_rows(self, per_edge: Tensor) -> Tensor:
+        """[E, k] per-edge rows (caller's edge order) -> CSR order."""
+        return ops.gather_rows(per_edge.contiguous(), self.perm)
+
+    def from_csr_order_rows(self, per_edge_csr: Tensor) -> Tensor:
+        if self._inv_perm is None:
+            self._inv_perm = self._inverse(self.perm)
+        return ops.gather_rows(per_edge_csr.contiguous(), self._inv_perm)
+
     @property
     def t2csr(self) -> Tensor:
         """CSR slot of every transposed-CSR slot (the reference's csr2csc / _T_perm role)."""

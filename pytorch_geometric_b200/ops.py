@@ -493,6 +493,97 @@ def gat_fused_csr_backward(rowptr, col, dst_of_edge, rowptr_t, col_t, t2csr, xh,
     return gxh, gas, gad
 
 
+ATTN_MODES = {"gat": 0, "gatv2": 1, "dot": 2}
+
+
+def attn_supported(heads: int, chan: int, dtype: torch.dtype) -> bool:
+    """True when [*, heads*chan] rows of `dtype` are on the vector path of csrc/attention.cu."""
+    if dtype not in (torch.float32, torch.bfloat16):
+        return False
+    return bool(lib().b200mp_attn_supported(heads, chan, BF16 if dtype == torch.bfloat16 else F32))
+
+
+def _row_stride(t: Optional[Tensor], hc: int) -> int:
+    """Row stride in elements of a [n, heads*chan] operand that may be a column slice of a wider matrix."""
+    if t is None:
+        return 0
+    if t.dim() != 2 or t.size(1) != hc or t.stride(1) != 1:
+        raise ValueError("attention operands must be [n, heads*chan] with unit inner stride")
+    return t.stride(0)
+
+
+def attn_forward(mode: str, rowptr: Tensor, col: Tensor, v: Tensor, heads: int, chan: int, *, k: Optional[Tensor] = None,
+                 q: Optional[Tensor] = None, s_src: Optional[Tensor] = None, s_dst: Optional[Tensor] = None,
+                 att: Optional[Tensor] = None, s_edge: Optional[Tensor] = None, slope: float = 0.2, scale: float = 1.0,
+                 want_alpha: bool = False, plan: Optional["LongRowPlan"] = None):
+    """Fused edge-softmax attention + aggregation (b200mp_attn_csr_forward).  v / k: [n_src, H*C] (column slices of
+    a wider matrix are fine), q: [n_rows, H*C].  Returns (out, row_max, row_den, alpha or None)."""
+    _cuda(rowptr, col, v, k, q, s_src, s_dst, att, s_edge)
+    it = _same_idx(rowptr, col)
+    hc = heads * chan
+    n_rows = rowptr.numel() - 1
+    out = torch.empty((n_rows, hc), dtype=v.dtype, device=v.device)
+    row_max = torch.empty((n_rows, heads), dtype=torch.float32, device=v.device)
+    row_den = torch.empty_like(row_max)
+    alpha = torch.empty((col.numel(), heads), dtype=torch.float32, device=v.device) if want_alpha else None
+    pargs, _part = _plan_args(plan, hc, v.device)
+    part_ms = torch.empty(plan.n_chunks * heads * 2, dtype=torch.float32, device=v.device) if pargs[2] else None
+    launches = 1 + (1 if pargs[2] else 0) + (1 if want_alpha else 0)
+    _timed("attn_forward", launches, lib().b200mp_attn_csr_forward, ATTN_MODES[mode], _p(rowptr), _p(col), _p(v), _p(k), _p(q),
+           _p(s_src), _p(s_dst), _p(att), _p(s_edge), _row_stride(v, hc), _row_stride(k, hc), _row_stride(q, hc), _p(out),
+           _p(row_max), _p(row_den), _p(alpha), n_rows, col.numel(), heads, chan, float(slope), float(scale), *pargs,
+           _p(part_ms), it, _vdt(v), _stream())
+    return out, row_max, row_den, alpha
+
+
+def attn_backward(mode: str, rowptr, col, rowptr_t, col_t, t2csr, v: Tensor, heads: int, chan: int, row_max, row_den, out,
+                  grad_out, *, k=None, q=None, s_src=None, s_dst=None, att=None, s_edge=None, slope: float = 0.2,
+                  scale: float = 1.0, plan=None, plan_t=None, grad_v: Optional[Tensor] = None,
+                  grad_k: Optional[Tensor] = None):
+    """Backward of attn_forward.  Returns a dict with grad_v, and per mode grad_k / grad_q / grad_s_src /
+    grad_s_dst / grad_att / grad_s_edge.  grad_v / grad_k may be preallocated (column slices of one matrix)."""
+    _cuda(rowptr, col, rowptr_t, col_t, t2csr, v, grad_out)
+    it = _same_idx(rowptr, col, rowptr_t, col_t, t2csr)
+    m = ATTN_MODES[mode]
+    hc = heads * chan
+    dev = v.device
+    n_rows, n_src, n_edges = rowptr.numel() - 1, rowptr_t.numel() - 1, col.numel()
+    grad_out = grad_out.contiguous()
+    out = out.contiguous()
+    pair = torch.empty((n_edges, heads, 2), dtype=torch.float32, device=dev)
+    if grad_v is None:
+        grad_v = torch.empty((n_src, hc), dtype=v.dtype, device=dev)
+    if m == 2 and grad_k is None:
+        grad_k = torch.empty((n_src, hc), dtype=v.dtype, device=dev)
+    if _row_stride(grad_v, hc) != _row_stride(v, hc) or (m == 2 and _row_stride(grad_k, hc) != _row_stride(k, hc)):
+        raise ValueError("grad_v / grad_k must have the row stride of v / k")
+    grad_q = torch.empty((n_rows, hc), dtype=v.dtype, device=dev) if m != 0 else None
+    if q is not None and _row_stride(q, hc) != hc:
+        q = q.contiguous()
+    gss = torch.empty((n_src, heads), dtype=torch.float32, device=dev) if m == 0 else None
+    gsd = torch.empty((n_rows, heads), dtype=torch.float32, device=dev) if m == 0 else None
+    gatt = gatt_part = None
+    if m == 1:
+        gatt = torch.empty(hc, dtype=torch.float32, device=dev)
+        gatt_part = torch.empty(int(lib().b200mp_attn_gatt_rows()) * hc, dtype=torch.float32, device=dev)
+    w = int(lib().b200mp_attn_backward_partial_width(m, heads, chan, 0))
+    wt = int(lib().b200mp_attn_backward_partial_width(m, heads, chan, 1))
+    if plan is not None and plan_t is plan:   # one plan object cannot describe both the CSR and its transpose
+        raise ValueError("pass distinct plans for the CSR and the transposed CSR")
+    pa, _keep = _plan_args(plan, w, dev)
+    pt, _keep_t = _plan_args(plan_t, wt, dev)
+    _timed("attn_backward", 2 + (1 if pa[2] else 0) + (1 if pt[2] else 0) + (1 if m == 1 else 0), lib().b200mp_attn_csr_backward, m,
+           _p(rowptr), _p(col), _p(rowptr_t), _p(col_t), _p(t2csr), _p(v), _p(k), _p(q), _p(s_src), _p(s_dst), _p(att),
+           _p(s_edge), _row_stride(v, hc), _row_stride(k, hc), _row_stride(q, hc), _p(row_max), _p(row_den), _p(out),
+           _p(grad_out), _p(pair), _p(grad_v), _p(grad_k), _p(grad_q), _p(gss), _p(gsd), _p(gatt), _p(gatt_part), n_rows,
+           n_src, n_edges, heads, chan, float(slope), float(scale), pa[0], pa[1], pa[2], pa[3], pa[4], pa[5], pt[0],
+           pt[1], pt[2], pt[3], pt[5], it, _vdt(v), _stream())
+    res = {"grad_v": grad_v, "grad_k": grad_k, "grad_q": grad_q, "grad_s_src": gss, "grad_s_dst": gsd, "grad_att": gatt}
+    if s_edge is not None:
+        res["grad_s_edge"] = pair[:, :, 1]
+    return res
+
+
 def column_sum(x: Tensor) -> Tensor:
     """sum over rows of a [n, F] matrix in fp32 (the bias gradient); deterministic, two launches."""
     _cuda(x)
