@@ -303,6 +303,18 @@ int b200mp_gat_fused_csr_backward(const void* rowptr, const void* col, const voi
                                   int64_t n_long_rows, int64_t n_chunks, int64_t chunk, float* partials,
                                   int idx_dtype, int val_dtype, void* stream);
 
+/* ------------------------------------------------------------------ argmin / argmax outputs (csrc/arg.cu)
+ * The (out, arg) operator signatures the reference binds to: torch_scatter.scatter_max / scatter_min
+ * (utils/_scatter.py:147-156) and torch.ops.torch_sparse.spmm_min / spmm_max (edge_index.py:1798-1810).
+ * `out` is what b200mp_scatter_coo / b200mp_spmm_csr produced (fp32, min or max); these passes find its producer:
+ *   b200mp_scatter_arg   arg[i,f] = smallest e with index[e] == i and src[e,f] == out[i,f]; n_src for empty groups
+ *   b200mp_spmm_csr_arg  arg[i,f] = first CSR slot e of row i with val[e]*x[col[e],f] == out[i,f]; nnz for empty rows
+ * arg: int64 [n_rows, feat]. */
+int b200mp_scatter_arg(const float* src, const void* index, const float* out, int64_t* arg, int64_t n_src,
+                       int64_t n_rows, int64_t feat, int idx_dtype, void* stream);
+int b200mp_spmm_csr_arg(const void* rowptr, const void* col, const float* val, const float* x, const float* out,
+                        int64_t* arg, int64_t n_rows, int64_t feat, int64_t nnz, int idx_dtype, void* stream);
+
 /* ------------------------------------------------------------------ fused attention family (csrc/attention.cu)
  * One kernel skeleton for the three score functions of the reference's attention convolutions, forward and
  * backward, over the destination-sorted CSR (alpha = softmax over the in-edges of i, utils/_softmax.py:82-88;
@@ -369,6 +381,18 @@ int64_t b200mp_linear_grad_weight_workspace_bytes(int64_t m, int64_t n, int64_t 
 int b200mp_linear_grad_weight_tf32x3(const float* g, const float* x, float* gw, int64_t m, int64_t n,
                                      int64_t k, void* workspace, int64_t workspace_bytes,
                                      void* stream);
+
+/* Pair form of the TS-mode kernel (A operand in tensor memory): two A streams accumulate into ONE TMEM accumulator,
+ * the epilogue adds a bias and applies ReLU, and the output columns may be split over two matrices:
+ *     [c1 | c2] [M, n1+n2] = act( [a1 | a2] [M, k1+k2] . B + bias )
+ * b_layout 0: B = w [n1+n2, k1+k2] row-major (y = A w^T: SAGEConv's lin_l(agg) + lin_r(x) with w = [W_l | W_r],
+ * sage_conv.py:134-141, in one launch instead of two GEMMs and an add); b_layout 1: B = w [k1+k2, n1+n2] row-major
+ * (y = A w: both input gradients of such a pair from one read of g, RGCNConv's [H | x] . [W_1;..;W_R; root],
+ * rgcn_conv.py:257-280).  a2 / c2 / bias nullable (k2 = 0 / n2 = 0).  k1, k2 % 32 == 0; n1, n2 % 128 == 0;
+ * b_lo == NULL: b_hi is the unsplit matrix (the kernel splits B tiles itself). */
+int b200mp_gemm_pair_tf32x3(const float* a1, int64_t k1, const float* a2, int64_t k2, const float* b_hi,
+                            const float* b_lo, int b_layout, const float* bias, int relu, float* c1, int64_t n1,
+                            float* c2, int64_t n2, int64_t m, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ _SIGS = {
     "b200mp_linear_grad_input_tf32x3": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "b200mp_linear_grad_weight_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "b200mp_linear_grad_weight_tf32x3": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _P]),
+    "b200mp_gemm_pair_tf32x3": (_INT, [_P, _I64, _P, _I64, _P, _P, _INT, _P, _INT, _P, _I64, _P, _I64, _I64, _P]),
     "b200mp_index_add_rows": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P]),
     "b200mp_gather_rows": (_INT, [_P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
     "b200mp_softmax_csr": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P]),
@@ -55,6 +56,8 @@ _SIGS = {
     "b200mp_gat_fused_csr": (_INT, [_P] * 10 + [_I64, _I64, _I64, _I64, _F, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _INT, _P]),
     "b200mp_gat_fused_csr_backward": (_INT, [_P] * 18 + [_I64, _I64, _I64, _I64, _I64, _F, _P, _P, _I64, _I64, _I64, _P,
                                               _INT, _INT, _P]),
+    "b200mp_scatter_arg": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _INT, _P]),
+    "b200mp_spmm_csr_arg": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _INT, _P]),
     "b200mp_attn_supported": (_INT, [_I64, _I64, _INT]),
     "b200mp_attn_csr_forward": (_INT, [_INT] + [_P] * 9 + [_I64] * 3 + [_P] * 4 + [_I64] * 4 + [_F, _F, _P, _P, _I64, _I64, _I64,
                                        _P, _P, _INT, _INT, _P]),

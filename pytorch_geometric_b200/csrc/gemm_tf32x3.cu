@@ -170,6 +170,12 @@ struct GemmArgs {
     int prefetch;         // L2 prefetch distance in k-blocks (0 = off)
     int debug;            // timing experiments only (results are WRONG when non-zero): bit0 = skip the hi/lo split,
                           // bit1 = issue only the hi*hi product, bit2 = epilogue skips the global stores
+    // ---- TS kernel only (zero-initialised elsewhere) ----
+    int k_blocks_a1;      // k-blocks [0, k_blocks_a1) stream from tmap_a, the rest from tmap_a2 (A = [a1 | a2] along K):
+                          // two products accumulate into ONE TMEM accumulator (SAGE: agg W_l^T + x W_r^T)
+    int n_tiles_c1;       // n-tiles [0, n_tiles_c1) are stored through tmap_c, the rest through tmap_c2 (two outputs)
+    const float* bias;    // epilogue: + bias[n] (nullable)
+    int relu;             // epilogue: max(., 0)
 };
 
 // A_MN / B_MN: operand is MN-major (stored row-major as [K, MN]); B_PRE: B arrives pre-split
@@ -490,20 +496,30 @@ int get_option_gemm_prefetch(); // L2 prefetch distance in k-blocks for the stre
 
 static bool width_ok(int64_t w) { return w == 64 || w == 128 || (w > 0 && w % 256 == 0); }
 
-// TS path (A in TMEM): y[M, n_out] = a[M, k_red] . B, K-major or MN-major B; b_lo == nullptr: b_hi is the
-// unsplit matrix and the kernel splits the B tiles itself
-static int run_ts(const float* a, const float* b_hi, const float* b_lo, float* c, int64_t m, int64_t n_out, int64_t k_red,
-                  bool b_mn, int64_t b_rows, int64_t b_cols, cudaStream_t s) {
-    CUtensorMap ta, tbh, tbl, tc;
+// TS path (A in TMEM): [c1 | c2][M, n1 + n2] = [a1 | a2][M, k1 + k2] . B (+ bias, relu), K-major or MN-major B;
+// b_lo == nullptr: b_hi is the unsplit matrix and the kernel splits the B tiles itself
+static int run_ts2(const float* a1, int64_t k1, const float* a2, int64_t k2, const float* b_hi, const float* b_lo, float* c1,
+                   int64_t n1, float* c2, int64_t n2, const float* bias, int relu, int64_t m, bool b_mn, cudaStream_t s) {
+    const int64_t k_red = k1 + k2, n_out = n1 + n2;
+    const int64_t b_rows = b_mn ? k_red : n_out, b_cols = b_mn ? n_out : k_red;
+    CUtensorMap ta, ta2, tbh, tbl, tc, tc2;
     int rc;
-    if ((rc = make_map(&tc, c, m, n_out, n_out, false, 32, 32))) return rc;      // output boxes [32 rows x 32 cols]
-    if ((rc = make_map(&ta, a, m, k_red, k_red, false, 32, kBM))) return rc;
+    if ((rc = make_map(&tc, c1, m, n1, n1, false, 32, 32))) return rc;           // output boxes [32 rows x 32 cols]
+    if ((rc = make_map(&tc2, c2 ? c2 : c1, m, c2 ? n2 : n1, c2 ? n2 : n1, false, 32, 32))) return rc;
+    if ((rc = make_map(&ta, a1, m, k1, k1, false, 32, kBM))) return rc;
+    if ((rc = make_map(&ta2, a2 ? a2 : a1, m, a2 ? k2 : k1, a2 ? k2 : k1, false, 32, kBM))) return rc;
     if ((rc = make_map(&tbh, b_hi, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
     if ((rc = make_map(&tbl, b_lo ? b_lo : b_hi, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
     const int kb = static_cast<int>(k_red / 32);
-    GemmArgs args{c, m, n_out, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n_out / kTsBN), kb, kb, 1, get_option_gemm_prefetch(), get_option_gemm_debug()};
-    if (!b_lo) return b_mn ? launch_gemm_ts<true, true>(ta, tbh, tbl, tc, args, s) : launch_gemm_ts<false, true>(ta, tbh, tbl, tc, args, s);
-    return b_mn ? launch_gemm_ts<true, false>(ta, tbh, tbl, tc, args, s) : launch_gemm_ts<false, false>(ta, tbh, tbl, tc, args, s);
+    GemmArgs args{c1, m, n_out, static_cast<int>(ceil_div(m, kBM)), static_cast<int>(n_out / kTsBN), kb, kb, 1,
+                  get_option_gemm_prefetch(), get_option_gemm_debug(), static_cast<int>(k1 / 32), static_cast<int>(n1 / kTsBN), bias, relu};
+    if (!b_lo) return b_mn ? launch_gemm_ts<true, true>(ta, ta2, tbh, tbl, tc, tc2, args, s) : launch_gemm_ts<false, true>(ta, ta2, tbh, tbl, tc, tc2, args, s);
+    return b_mn ? launch_gemm_ts<true, false>(ta, ta2, tbh, tbl, tc, tc2, args, s) : launch_gemm_ts<false, false>(ta, ta2, tbh, tbl, tc, tc2, args, s);
+}
+static int run_ts(const float* a, const float* b_hi, const float* b_lo, float* c, int64_t m, int64_t n_out, int64_t k_red,
+                  bool b_mn, int64_t b_rows, int64_t b_cols, cudaStream_t s) {
+    (void)b_rows; (void)b_cols;
+    return run_ts2(a, k_red, nullptr, 0, b_hi, b_lo, c, n_out, nullptr, 0, nullptr, 0, m, b_mn, s);
 }
 
 // y[M,N] = x[M,K] . w[N,K]^T
@@ -639,4 +655,19 @@ extern "C" int b200mp_linear_grad_weight_tf32x3(const float* g, const float* x, 
     }
     return get_option_gemm_bk() == 32 ? run_grad_weight<32>(g, x, gw, m, n, k, workspace, workspace_bytes, s)
                                       : run_grad_weight<16>(g, x, gw, m, n, k, workspace, workspace_bytes, s);
+}
+
+extern "C" int b200mp_gemm_pair_tf32x3(const float* a1, int64_t k1, const float* a2, int64_t k2, const float* b_hi,
+                                       const float* b_lo, int b_layout, const float* bias, int relu, float* c1, int64_t n1,
+                                       float* c2, int64_t n2, int64_t m, void* stream) {
+    B200MP_CHECK_ARG(m >= 0 && k1 > 0 && k2 >= 0 && n1 > 0 && n2 >= 0 && (b_layout == 0 || b_layout == 1));
+    if (m == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(a1 && b_hi && c1 && ok16(a1) && ok16(a2) && ok16(b_hi) && ok16(b_lo) && ok16(c1) && ok16(c2));
+    B200MP_CHECK_ARG((k2 == 0) == (a2 == nullptr) && (n2 == 0) == (c2 == nullptr));
+    if (k1 % 32 != 0 || k2 % 32 != 0 || n1 % kTsBN != 0 || n2 % kTsBN != 0 || m > 0x7fffffffLL) {
+        set_error("gemm_pair_tf32x3: unsupported shape m=%lld k=%lld+%lld n=%lld+%lld (k %% 32, n %% 128)", (long long)m,
+                  (long long)k1, (long long)k2, (long long)n1, (long long)n2);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    return run_ts2(a1, k1, a2, k2, b_hi, b_lo, c1, n1, c2, n2, bias, relu, m, b_layout == 1, static_cast<cudaStream_t>(stream));
 }

@@ -56,9 +56,9 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uin
 
 template <bool B_MN, bool B_SPLIT>
 __global__ void __launch_bounds__(kGemmThreadsTs, 1)
-gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_hi,
-                      const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_c,
-                      GemmArgs args) {
+gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                      const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
+                      const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2, GemmArgs args) {
     constexpr int BN = kTsBN, BK = 32, kStages = kTsStages;
     constexpr uint32_t kSlab = BK * 128;
     constexpr uint32_t kABytes = kBM * BK * 4;                  // raw fp32 A tile (K-major, 128B swizzle)
@@ -126,14 +126,16 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                             pm0 = (wn / args.n_tiles_n) * kBM;
                             ok = wn < n_work && pk < args.k_blocks && pm0 != m0;
                         }
-                        if (ok) tma_prefetch_2d(&tmap_a, pk * BK, pm0);
+                        if (ok && pk < args.k_blocks_a1) tma_prefetch_2d(&tmap_a, pk * BK, pm0);
                     }
                     bar_wait(bar_empty(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * kStageBytes;
                     const uint32_t sb_hi = sa + kABytes;
                     const uint32_t sb_lo = sb_hi + kBBytes;
                     bar_expect_tx(bar_full(stage), kTxBytes);
-                    tma_load_2d(sa, &tmap_a, kb * BK, m0, bar_full(stage));
+                    // A = [a1 | a2] along K: the two products of a pair (agg W_l^T + x W_r^T) share one accumulator
+                    if (kb < args.k_blocks_a1) tma_load_2d(sa, &tmap_a, kb * BK, m0, bar_full(stage));
+                    else tma_load_2d(sa, &tmap_a2, (kb - args.k_blocks_a1) * BK, m0, bar_full(stage));
                     // B_SPLIT: tmap_b_hi describes the unsplit matrix; its tile lands in the hi buffer
                     if (B_MN) {
 #pragma unroll
@@ -252,11 +254,22 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             // TMEM -> registers -> swizzled smem box -> TMA store: every global write is a full 128-byte
             // line issued by the copy engine (the thread-per-row direct stores cost 29 % of the kernel).
             const uint32_t my_stage = staging + static_cast<uint32_t>(q) * 8192u;
+            const bool second = (w % args.n_tiles_n) >= args.n_tiles_c1;                // which of the two outputs
+            const CUtensorMap* cmap = second ? &tmap_c2 : &tmap_c;
+            const int cn0 = second ? n0 - args.n_tiles_c1 * BN : n0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const uint32_t buf = my_stage + static_cast<uint32_t>((c0 >> 5) & 1) * 4096u;
                 uint32_t r[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c0), r);
+                if (args.bias) {                                                      // fused epilogue: + bias[n] (, ReLU)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(args.bias + n0 + c0 + j));
+                }
+                if (args.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.0f));
+                }
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this box's previous store has read it
                 __syncwarp();
                 if (!(args.debug & 4)) {
@@ -266,7 +279,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                               r[4 * c + 2], r[4 * c + 3]);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) tma_store_2d(&tmap_c, n0 + c0, static_cast<int>(m0) + q * 32, buf);
+                    if (lane == 0) tma_store_2d(cmap, cn0 + c0, static_cast<int>(m0) + q * 32, buf);
                 }
             }
             tc_fence_before();
@@ -281,14 +294,14 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 }
 
 template <bool B_MN, bool B_SPLIT>
-static int launch_gemm_ts(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const CUtensorMap& tc,
-                          const GemmArgs& args, cudaStream_t stream) {
+static int launch_gemm_ts(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tbh, const CUtensorMap& tbl,
+                          const CUtensorMap& tc, const CUtensorMap& tc2, const GemmArgs& args, cudaStream_t stream) {
     constexpr size_t smem = kTsStages * (kBM * 32 * 4 + 2 * kTsBN * 32 * 4) + 4 * 2 * 4096 + 256 + 1024;
     auto kfn = gemm_tf32x3_ts_kernel<B_MN, B_SPLIT>;
     B200MP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int n_work = args.n_tiles_m * args.n_tiles_n;
     const int grid = n_work < num_sms() ? n_work : num_sms();
-    kfn<<<grid, kGemmThreadsTs, smem, stream>>>(ta, tbh, tbl, tc, args);
+    kfn<<<grid, kGemmThreadsTs, smem, stream>>>(ta, ta2, tbh, tbl, tc, tc2, args);
     B200MP_LAUNCH_CHECK();
     return B200MP_OK;
 }

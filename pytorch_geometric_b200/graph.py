@@ -66,10 +66,51 @@ class CSRGraph:
         return cls(edge_index[0], edge_index[1], num_src if num_src is not None else num_nodes,
                    num_dst if num_dst is not None else num_nodes, edge_weight, **kw)
 
+    @classmethod
+    def from_csr(cls, rowptr: Tensor, col: Tensor, num_src: int, edge_weight: Optional[Tensor] = None,
+                 transposed: Optional[tuple] = None, chunk: int = DEFAULT_CHUNK,
+                 idx_dtype: Optional[torch.dtype] = None) -> "CSRGraph":
+        """Adopts an EXISTING destination-sorted CSR -- an `EdgeIndex`'s cached `(indptr, other index)`
+        (edge_index.py:626-696), a `torch.sparse_csr` tensor's `(crow_indices, col_indices)`, a loader's `ptr` --
+        without sorting anything: the caller's edge order IS the CSR order (`perm` = identity, stored as None).
+        `transposed` = (rowptr_t, col_t, perm_t) adopts the cached transposed structure as well (the reference's
+        `_T_indptr`, `_T_index`, `_T_perm`), otherwise it is built on first use by one stable sort.
+        Indices are converted to int32 once when everything fits (a streaming pass, not a sort)."""
+        if not rowptr.is_cuda:
+            raise RuntimeError("CSRGraph lives on a CUDA device (no CPU fallback)")
+        g = object.__new__(cls)
+        E, n_dst = col.numel(), rowptr.numel() - 1
+        if idx_dtype is None:
+            idx_dtype = torch.int32 if max(num_src, n_dst, E) < _INT32_MAX else torch.int64
+        g.idx_dtype = idx_dtype
+        g.num_src, g.num_dst, g.num_edges = int(num_src), int(n_dst), int(E)
+        g.chunk, g.device = int(chunk), rowptr.device
+        g.rowptr = ops.convert_index(rowptr.contiguous(), idx_dtype)
+        g.col = ops.convert_index(col.contiguous(), idx_dtype)
+        g.perm = None
+        g._src, g._dst = g.col, None                          # _dst = ptr2index(rowptr), materialised on demand
+        g.val = None if edge_weight is None else edge_weight.detach().float().contiguous()
+        g.plan = ops.LongRowPlan(g.rowptr, g.chunk)
+        g._t_built = False
+        g.perm_t = g.rowptr_t = g.col_t = g.val_t = g.plan_t = None
+        g._mean_val_t = g._inv_perm = g._inv_perm_t = g._dst_csr = g._t2csr = None
+        if transposed is not None:
+            rowptr_t, col_t, perm_t = transposed
+            g.rowptr_t = ops.convert_index(rowptr_t.contiguous(), idx_dtype)
+            g.col_t = ops.convert_index(col_t.contiguous(), idx_dtype)
+            g.perm_t = ops.convert_index(perm_t.contiguous(), idx_dtype)
+            g.plan_t = ops.LongRowPlan(g.rowptr_t, g.chunk)
+            g._t_built = True
+            if g.val is not None:
+                g.val_t = ops.permute(g.val, g.perm_t)
+        return g
+
     # ------------------------------------------------------------------ transposed structure
     def build_transpose(self) -> None:
         if self._t_built:
             return
+        if self._dst is None:
+            self._dst = self.dst_csr
         _, self.perm_t, self.rowptr_t = ops.sort_by_key(self._src, self.num_src, want_sorted=False)
         self.col_t = ops.permute(self._dst, self.perm_t)
         self.plan_t = ops.LongRowPlan(self.rowptr_t, self.chunk)
@@ -79,6 +120,8 @@ class CSRGraph:
 
     # per-edge tensor permutations (1-D fp32 / int tensors)
     def to_csr_order(self, per_edge: Tensor) -> Tensor:
+        if self.perm is None:                                   # adopted CSR: the caller's order is the CSR order
+            return per_edge.contiguous()
         return ops.permute(per_edge.contiguous(), self.perm)
 
     def to_csc_order(self, per_edge: Tensor) -> Tensor:
@@ -91,6 +134,8 @@ class CSRGraph:
         return inv
 
     def from_csr_order(self, per_edge_csr: Tensor) -> Tensor:
+        if self.perm is None:
+            return per_edge_csr.contiguous()
         if self._inv_perm is None:
             self._inv_perm = self._inverse(self.perm)
         return ops.permute(per_edge_csr.contiguous(), self._inv_perm)
@@ -103,9 +148,13 @@ class CSRGraph:
 
     def to_csr_order_rows(self, per_edge: Tensor) -> Tensor:
         """[E, k] per-edge rows (caller's edge order) -> CSR order."""
+        if self.perm is None:
+            return per_edge.contiguous()
         return ops.gather_rows(per_edge.contiguous(), self.perm)
 
     def from_csr_order_rows(self, per_edge_csr: Tensor) -> Tensor:
+        if self.perm is None:
+            return per_edge_csr.contiguous()
         if self._inv_perm is None:
             self._inv_perm = self._inverse(self.perm)
         return ops.gather_rows(per_edge_csr.contiguous(), self._inv_perm)
@@ -115,9 +164,12 @@ class CSRGraph:
         """CSR slot of every transposed-CSR slot (the reference's csr2csc / _T_perm role)."""
         if getattr(self, "_t2csr", None) is None:
             self.build_transpose()
-            if self._inv_perm is None:
-                self._inv_perm = self._inverse(self.perm)
-            self._t2csr = ops.permute(self._inv_perm, self.perm_t)
+            if self.perm is None:                                # CSR slot == caller's edge id
+                self._t2csr = self.perm_t
+            else:
+                if self._inv_perm is None:
+                    self._inv_perm = self._inverse(self.perm)
+                self._t2csr = ops.permute(self._inv_perm, self.perm_t)
         return self._t2csr
 
     @property
@@ -159,3 +211,47 @@ class CSRGraph:
     def __repr__(self) -> str:
         return (f"CSRGraph(num_src={self.num_src}, num_dst={self.num_dst}, num_edges={self.num_edges}, "
                 f"idx={self.idx_dtype}, long_rows={self.plan.n_long}, chunks={self.plan.n_chunks})")
+
+
+# ---------------------------------------------------------------------------------------------- graphs cached by tensor identity
+_GRAPH_CACHE: "dict" = {}
+_GRAPH_CACHE_EDGES = 600_000_000        # evict oldest entries above this many cached edges
+
+
+def _cache_put(key, holders, graph) -> None:
+    _GRAPH_CACHE[key] = (holders, graph)
+    total = sum(g.num_edges for _, g in _GRAPH_CACHE.values())
+    while total > _GRAPH_CACHE_EDGES and len(_GRAPH_CACHE) > 1:
+        k0 = next(iter(_GRAPH_CACHE))
+        total -= _GRAPH_CACHE.pop(k0)[1].num_edges
+
+
+def cached_graph(edge_index: Tensor, num_src: int, num_dst: int, flow: str = "source_to_target", loops: Optional[str] = None,
+                 loop_nodes: Optional[int] = None, edge_type: Optional[Tensor] = None,
+                 num_relations: Optional[int] = None) -> CSRGraph:
+    """The CSRGraph of a `[2, E]` edge_index, built once per tensor (storage pointer + length + version counter; the
+    cache entry keeps the tensor alive so the pointer cannot be reused) -- what `cached=True` does for GCNConv in the
+    reference (gcn_conv.py:150-158), for every layer.  loops='gat': remove_self_loops + add_self_loops for the first
+    `loop_nodes` nodes (gat_conv.py:334-346).  edge_type / num_relations: the relational graph of RGCNConv, keyed by
+    the virtual destination dst * R + type."""
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must have shape [2, E]")
+    key = (edge_index.data_ptr(), edge_index.numel(), edge_index._version, int(num_src), int(num_dst), flow, loops, loop_nodes,
+           None if edge_type is None else (edge_type.data_ptr(), edge_type._version), num_relations)
+    hit = _GRAPH_CACHE.get(key)
+    if hit is not None:
+        return hit[1]
+    ei = edge_index
+    if loops == "gat":
+        from . import utils as U
+        ei = U.remove_then_add_self_loops(edge_index, int(loop_nodes if loop_nodes is not None else min(num_src, num_dst)))
+    src, dst = (ei[0], ei[1]) if flow == "source_to_target" else (ei[1], ei[0])
+    if edge_type is not None:
+        dst = dst.to(torch.int64) * int(num_relations) + edge_type.to(torch.int64)
+    g = CSRGraph(src, dst, num_src, num_dst)
+    _cache_put(key, (edge_index, edge_type), g)
+    return g
+
+
+def clear_graph_cache() -> None:
+    _GRAPH_CACHE.clear()

@@ -376,6 +376,36 @@ def scatter_coo(src: Tensor, index: Tensor, n_rows: int, reduce: str = "sum") ->
     return out.view((n_rows, ) + tuple(src.shape[1:]))
 
 
+def scatter_arg(src: Tensor, index: Tensor, out: Tensor) -> Tensor:
+    """arg[i,f] = smallest e with index[e] == i and src[e,f] == out[i,f] (src.size(0) for empty groups): the second
+    output of torch_scatter.scatter_max / scatter_min for an `out` computed by scatter_coo(min / max)."""
+    _cuda(src, index, out)
+    if src.dtype != torch.float32 or out.dtype != torch.float32:
+        raise TypeError("scatter_arg is fp32 only")
+    src, index, out = src.contiguous(), index.contiguous(), out.contiguous()
+    flat, oflat = src.view(src.size(0), -1), out.view(out.size(0), -1)
+    arg = torch.empty(oflat.shape, dtype=torch.int64, device=src.device)
+    _timed("scatter_arg", 2, lib().b200mp_scatter_arg, _p(flat), _p(index), _p(oflat), _p(arg), flat.size(0), oflat.size(0),
+           flat.size(1), _idt(index), _stream())
+    return arg.view(out.shape)
+
+
+def spmm_csr_arg(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, out: Tensor) -> Tensor:
+    """arg[i,f] = first CSR slot of row i whose (weighted) value equals out[i,f] (nnz for empty rows): the second
+    output of torch.ops.torch_sparse.spmm_min / spmm_max."""
+    _cuda(rowptr, col, val, x, out)
+    if x.dtype != torch.float32 or out.dtype != torch.float32:
+        raise TypeError("spmm_csr_arg is fp32 only")
+    it = _same_idx(rowptr, col)
+    x, out = x.contiguous(), out.contiguous()
+    if val is not None:
+        val = val.contiguous().float()
+    arg = torch.empty(out.shape, dtype=torch.int64, device=x.device)
+    _timed("spmm_csr_arg", 1, lib().b200mp_spmm_csr_arg, _p(rowptr), _p(col), _p(val), _p(x), _p(out), _p(arg), out.size(0),
+           out.size(1), col.numel(), it, _stream())
+    return arg
+
+
 def index_add_rows(out: Tensor, index: Tensor, src: Tensor) -> Tensor:
     """out[index[e], :] += src[e, :] in place (fp32, atomics)."""
     _cuda(out, index, src)

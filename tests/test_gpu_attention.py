@@ -121,19 +121,41 @@ def test_dot_attention_with_fused_key_value_matrix():
     assert torch.equal(kv.grad[:, :H * C], k2.grad) and torch.equal(kv.grad[:, H * C:], v2.grad)
 
 
-def test_gatv2_attention_vs_oracle_and_golden():
+def test_gatv2_attention_vs_oracle_and_golden_layer():
+    """(1) the fused attention on the golden's projected inputs against the oracle's restatement of
+    gatv2_conv.py:310-378 (H = 4, C = 3: off the vector path -> zero-padded heads); (2) the whole GATv2Conv layer,
+    forward and backward, against what the reference's GATv2Conv produced (tests/golden/gatv2.npz)."""
+    from pytorch_geometric_b200.nn import GATv2Conv
     g = load_golden("gatv2")
     H, C = int(g["H"]), int(g["C"])
-    x_l, x_r = g["x_l"], g["x_r"]
-    N = x_l.shape[0]
-    out_ref, alpha_ref, r2, c2 = O.gatv2_attention(x_l.reshape(N, H, C), x_r.reshape(N, H, C), g["att"].reshape(H, C),
-                                                   g["ei"][0], g["ei"][1], 0.2, add_self_loops=True)
     cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)          # noqa: E731
-    graph = CSRGraph(cu(r2), cu(c2), N, N)
-    out, alpha = Fn.attention("gatv2", graph, H, C, v=cu(x_l.reshape(N, H * C)), q=cu(x_r.reshape(N, H * C)),
-                              att=cu(g["att"].reshape(-1)), negative_slope=0.2, return_alpha=True)
-    np.testing.assert_allclose(out.cpu().numpy(), out_ref.reshape(N, H * C), rtol=1e-5, atol=1e-6)
-    perm = graph.perm.cpu().numpy().astype(np.int64)
-    np.testing.assert_allclose(alpha.cpu().numpy(), alpha_ref[perm], rtol=1e-5, atol=1e-7)
-    # the golden holds what the reference's GATv2Conv itself produced from the same projected inputs
-    np.testing.assert_allclose(out.cpu().numpy(), g["attn_out"].reshape(N, H * C), rtol=1e-5, atol=1e-6)
+    for tag, share in (("sep", False), ("shared", True)):
+        x = g["x"]
+        N = x.shape[0]
+        x_l = x @ g[f"{tag}_lin_l_w"].T + g[f"{tag}_lin_l_b"]
+        x_r = x @ g[f"{tag}_lin_r_w"].T + g[f"{tag}_lin_r_b"]
+        out_ref, alpha_ref, r2, c2 = O.gatv2_attention(x_l.reshape(N, H, C), x_r.reshape(N, H, C), g[f"{tag}_att"],
+                                                       g["ei"][0], g["ei"][1], 0.2, add_self_loops=True)
+        graph = CSRGraph(cu(r2), cu(c2), N, N)
+        out, alpha = Fn.attention("gatv2", graph, H, C, v=cu(x_l.astype(np.float32)), q=cu(x_r.astype(np.float32)),
+                                  att=cu(g[f"{tag}_att"].reshape(-1)), negative_slope=0.2, return_alpha=True)
+        np.testing.assert_allclose(out.cpu().numpy(), out_ref.reshape(N, H * C), rtol=2e-5, atol=2e-6)
+        perm = graph.perm.cpu().numpy().astype(np.int64)
+        np.testing.assert_allclose(alpha.cpu().numpy(), alpha_ref[perm], rtol=2e-5, atol=1e-6)
+        # ---- the layer against the reference's own run
+        conv = GATv2Conv(x.shape[1], C, heads=H, share_weights=share).to(DEV)
+        with torch.no_grad():
+            conv.lin_l.weight.copy_(cu(g[f"{tag}_lin_l_w"]))
+            conv.lin_l.bias.copy_(cu(g[f"{tag}_lin_l_b"]))
+            if not share:
+                conv.lin_r.weight.copy_(cu(g[f"{tag}_lin_r_w"]))
+                conv.lin_r.bias.copy_(cu(g[f"{tag}_lin_r_b"]))
+            conv.att.copy_(cu(g[f"{tag}_att"]).view(1, H, C))
+            conv.bias.copy_(cu(g[f"{tag}_bias"]))
+        xt = cu(x).requires_grad_()
+        y = conv(xt, cu(g["ei"]))
+        np.testing.assert_allclose(y.detach().cpu().numpy(), g[f"{tag}_out"], rtol=2e-5, atol=2e-6)
+        y.backward(cu(g[f"{tag}_gout"]))
+        np.testing.assert_allclose(xt.grad.cpu().numpy(), g[f"{tag}_gx"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(conv.att.grad.view(H, C).cpu().numpy(), g[f"{tag}_g_att"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(conv.lin_l.weight.grad.cpu().numpy(), g[f"{tag}_g_lin_l_w"], rtol=1e-4, atol=1e-5)
