@@ -621,6 +621,8 @@ def main():
     ap.add_argument("--gemm-mode", type=int, default=-1, help="0 = SS-mode GEMM, 1 = TS-mode (A in TMEM); -1 = library default")
     ap.add_argument("--gemm-bsplit", type=int, default=-1,
                     help="1 = the GEMM kernel splits W tiles itself (one L2 read of W per tile), 0 = pre-split W_hi / W_lo")
+    ap.add_argument("--config", type=int, default=0,
+                    help="0 = the headline (GCNConv); 2 / 3 / 5 = the other single-box BASELINE configs (benchmarks/configs.py)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check after the timed loop")
@@ -633,7 +635,11 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-        run_b200(args)
+        if args.config:
+            from benchmarks import configs
+            configs.run_config(args, sys.modules[__name__])
+        else:
+            run_b200(args)
 
 
 if __name__ == "__main__":

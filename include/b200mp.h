@@ -394,6 +394,18 @@ int b200mp_gemm_pair_tf32x3(const float* a1, int64_t k1, const float* a2, int64_
                             const float* b_lo, int b_layout, const float* bias, int relu, float* c1, int64_t n1,
                             float* c2, int64_t n2, int64_t m, void* stream);
 
+/* Grouped form: pyg_lib.ops.segment_matmul(inputs, ptr, other) (nn/dense/linear.py:248-255, nn/conv/rgcn_conv.py:288;
+ * HeteroLinear, HeteroDictLinear, RGCNConv's sorted-by-type path).
+ *     c[ptr[r] : ptr[r+1], :] = a[ptr[r] : ptr[r+1], :] . B_r        for r in [0, n_seg)
+ * in ONE persistent launch over (segment, 128-row tile, 128-column tile) work items; ptr [n_seg+1] int64 stays on the
+ * device (the tile -> segment map is rebuilt in shared memory), partial tiles at segment ends are stored row-masked.
+ * b_layout 1: B_r = w[r] of a [n_seg, K, N] weight (c = a w[r]); b_layout 0: B_r = w[r] of a [n_seg, N, K] weight
+ * (c = a w[r]^T: the input gradient of layout 1).  b_hi / b_lo from b200mp_split_tf32 over the whole stack.
+ * k % 32 == 0, n % 128 == 0, n_seg <= 1024. */
+int b200mp_segment_matmul_tf32x3(const float* a, const int64_t* ptr, int64_t n_seg, const float* b_hi,
+                                 const float* b_lo, int b_layout, float* c, int64_t m, int64_t k, int64_t n,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

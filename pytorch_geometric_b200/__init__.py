@@ -6,7 +6,7 @@ graph.py (cached CSR/CSC structure), functional.py (autograd), utils.py / nn/ (h
 the reference's interface for this path), dist.py (node-range sharding + halo exchange),
 install.py (plugs the engine into an installed torch_geometric).
 """
-from . import ops, utils  # noqa: F401
+from . import minibatch, ops, utils  # noqa: F401
 from .functional import aggregate, scatter_coo, segment, softmax_csr  # noqa: F401
 from .graph import CSRGraph  # noqa: F401
 from ._lib import B200MPError, header_symbols, lib  # noqa: F401

@@ -49,6 +49,7 @@ _SIGS = {
     "b200mp_linear_grad_weight_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "b200mp_linear_grad_weight_tf32x3": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _P]),
     "b200mp_gemm_pair_tf32x3": (_INT, [_P, _I64, _P, _I64, _P, _P, _INT, _P, _INT, _P, _I64, _P, _I64, _I64, _P]),
+    "b200mp_segment_matmul_tf32x3": (_INT, [_P, _P, _I64, _P, _P, _INT, _P, _I64, _I64, _I64, _P]),
     "b200mp_index_add_rows": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P]),
     "b200mp_gather_rows": (_INT, [_P, _P, _P, _P, _I64, _I64, _INT, _INT, _P]),
     "b200mp_softmax_csr": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P]),

@@ -176,6 +176,10 @@ struct GemmArgs {
     int n_tiles_c1;       // n-tiles [0, n_tiles_c1) are stored through tmap_c, the rest through tmap_c2 (two outputs)
     const float* bias;    // epilogue: + bias[n] (nullable)
     int relu;             // epilogue: max(., 0)
+    // ---- grouped (segment_matmul) form of the TS kernel ----
+    const int64_t* seg_ptr;   // [n_seg + 1] row offsets of the segments of A / C (device memory: no host read of the sizes)
+    int n_seg;                // segment r multiplies with B block r
+    int b_seg_rows;           // rows of the stacked B matrix per segment (K for a [R, K, N] weight read MN-major, N_out K-major)
 };
 
 // A_MN / B_MN: operand is MN-major (stored row-major as [K, MN]); B_PRE: B arrives pre-split
@@ -670,4 +674,35 @@ extern "C" int b200mp_gemm_pair_tf32x3(const float* a1, int64_t k1, const float*
         return B200MP_ERR_UNSUPPORTED;
     }
     return run_ts2(a1, k1, a2, k2, b_hi, b_lo, c1, n1, c2, n2, bias, relu, m, b_layout == 1, static_cast<cudaStream_t>(stream));
+}
+
+// out[ptr[r] : ptr[r+1]] = a[ptr[r] : ptr[r+1]] . B_r for every segment r in ONE persistent launch: work items are
+// (segment, 128-row tile inside the segment, 128-column tile); the tile -> segment map is rebuilt in shared memory from
+// the device-resident ptr, so the segment sizes never travel to the host.
+extern "C" int b200mp_segment_matmul_tf32x3(const float* a, const int64_t* ptr, int64_t n_seg, const float* b_hi, const float* b_lo,
+                                            int b_layout, float* c, int64_t m, int64_t k, int64_t n, void* stream) {
+    B200MP_CHECK_ARG(m >= 0 && k > 0 && n > 0 && n_seg > 0 && (b_layout == 0 || b_layout == 1));
+    if (m == 0) return B200MP_OK;
+    B200MP_CHECK_ARG(a && ptr && b_hi && b_lo && c && ok16(a) && ok16(b_hi) && ok16(b_lo) && ok16(c));
+    if (k % 32 != 0 || n % kTsBN != 0 || n_seg > 1024 || m > 0x7fffffffLL) {
+        set_error("segment_matmul_tf32x3: unsupported shape m=%lld k=%lld n=%lld segments=%lld (k %% 32, n %% 128, <= 1024 segments)",
+                  (long long)m, (long long)k, (long long)n, (long long)n_seg);
+        return B200MP_ERR_UNSUPPORTED;
+    }
+    const bool b_mn = b_layout == 1;                       // 1: B_r = w[r] [K, N] row-major (out = a w[r]); 0: B_r = w[r] [N, K] (out = a w[r]^T)
+    const int64_t b_rows = n_seg * (b_mn ? k : n), b_cols = b_mn ? n : k;
+    CUtensorMap ta, tbh, tbl, tc;
+    int rc;
+    if ((rc = make_map(&tc, c, m, n, n, false, 32, 32))) return rc;
+    if ((rc = make_map(&ta, a, m, k, k, false, 32, kBM))) return rc;
+    if ((rc = make_map(&tbh, b_hi, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
+    if ((rc = make_map(&tbl, b_lo, b_rows, b_cols, b_cols, b_mn, 32, kTsBN))) return rc;
+    const int kb = static_cast<int>(k / 32);
+    // upper bound of the work list: every segment adds at most one partial tile
+    const int64_t max_tiles = ceil_div(m, kBM) + n_seg;
+    GemmArgs args{c, m, n, static_cast<int>(max_tiles), static_cast<int>(n / kTsBN), kb, kb, 1, 0, get_option_gemm_debug(),
+                  kb, static_cast<int>(n / kTsBN), nullptr, 0, ptr, static_cast<int>(n_seg), static_cast<int>(b_mn ? k : n)};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return b_mn ? launch_gemm_ts<true, false, true>(ta, ta, tbh, tbl, tc, tc, args, s)
+                : launch_gemm_ts<false, false, true>(ta, ta, tbh, tbl, tc, tc, args, s);
 }

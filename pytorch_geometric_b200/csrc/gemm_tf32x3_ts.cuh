@@ -54,7 +54,33 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uin
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool B_MN, bool B_SPLIT>
+// GROUPED: segment_matmul -- the row space is cut into segments (args.seg_ptr), every segment multiplies with its own B
+// block; tiles never straddle a segment (the last tile of a segment is partial and is stored with row-masked writes).
+struct GroupedTile {
+    int m0, n0, seg, rows;     // first row, first column, segment, valid rows (<= 128)
+};
+template <bool GROUPED>
+__device__ __forceinline__ bool ts_decode(int w, const GemmArgs& args, const int* tile_prefix, GroupedTile& t) {
+    const int mt = w / args.n_tiles_n;
+    t.n0 = (w % args.n_tiles_n) * kTsBN;
+    if (!GROUPED) {
+        t.m0 = mt * kBM;
+        t.seg = 0;
+        t.rows = kBM;
+        return true;
+    }
+    int r = 0;
+    while (r < args.n_seg && tile_prefix[r + 1] <= mt) ++r;          // few segments: a linear scan of shared memory
+    if (r >= args.n_seg) return false;
+    const int64_t s0 = args.seg_ptr[r], s1 = args.seg_ptr[r + 1];
+    const int64_t m0 = s0 + static_cast<int64_t>(mt - tile_prefix[r]) * kBM;
+    t.m0 = static_cast<int>(m0);
+    t.seg = r;
+    t.rows = static_cast<int>(s1 - m0 < kBM ? s1 - m0 : kBM);
+    return true;
+}
+
+template <bool B_MN, bool B_SPLIT, bool GROUPED = false>
 __global__ void __launch_bounds__(kGemmThreadsTs, 1)
 gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                       const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
@@ -86,6 +112,15 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    __shared__ int tile_prefix[GROUPED ? 1026 : 1];
+    if (GROUPED && threadIdx.x == 64) {                          // (an idle warp) tiles of 128 rows per segment, exclusive prefix
+        int acc = 0;
+        for (int r = 0; r < args.n_seg; ++r) {
+            tile_prefix[r] = acc;
+            acc += static_cast<int>((args.seg_ptr[r + 1] - args.seg_ptr[r] + kBM - 1) / kBM);
+        }
+        tile_prefix[args.n_seg] = acc;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             bar_init(bar_full(s), 1);
@@ -105,17 +140,20 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t tmem_base = *tmem_slot_gen;
     const uint32_t tmem_a0 = tmem_base + kAccCols;              // A slots start after the accumulators
 
-    const int n_work = args.n_tiles_m * args.n_tiles_n;         // n fastest: the two halves of a row block are adjacent
+    // n fastest: the two halves of a row block are adjacent
+    const int n_work = (GROUPED ? tile_prefix[args.n_seg] : args.n_tiles_m) * args.n_tiles_n;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int m0 = (w / args.n_tiles_n) * kBM;
-                const int n0 = (w % args.n_tiles_n) * BN;
+                GroupedTile gt;
+                ts_decode<GROUPED>(w, args, tile_prefix, gt);
+                const int m0 = gt.m0, n0 = gt.n0;
+                const int b_row0 = GROUPED ? gt.seg * args.b_seg_rows : 0;       // this segment's block of the stacked B
                 for (int kb = 0; kb < args.k_blocks; ++kb) {
-                    if (args.prefetch > 0 && n0 == 0) {
+                    if (!GROUPED && args.prefetch > 0 && n0 == 0) {
                         // A tiles of this row block's later k-blocks / of this CTA's next row block into L2.
                         // (n fastest: a row block is visited n_tiles_n times in a row, prefetch it once)
                         int pk = kb + args.prefetch, pm0 = m0;
@@ -140,12 +178,12 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     if (B_MN) {
 #pragma unroll
                         for (int s = 0; s < BN / 32; ++s) {
-                            tma_load_2d(sb_hi + s * kSlab, &tmap_b_hi, n0 + 32 * s, kb * BK, bar_full(stage));
-                            if (!B_SPLIT) tma_load_2d(sb_lo + s * kSlab, &tmap_b_lo, n0 + 32 * s, kb * BK, bar_full(stage));
+                            tma_load_2d(sb_hi + s * kSlab, &tmap_b_hi, n0 + 32 * s, b_row0 + kb * BK, bar_full(stage));
+                            if (!B_SPLIT) tma_load_2d(sb_lo + s * kSlab, &tmap_b_lo, n0 + 32 * s, b_row0 + kb * BK, bar_full(stage));
                         }
                     } else {
-                        tma_load_2d(sb_hi, &tmap_b_hi, kb * BK, n0, bar_full(stage));
-                        if (!B_SPLIT) tma_load_2d(sb_lo, &tmap_b_lo, kb * BK, n0, bar_full(stage));
+                        tma_load_2d(sb_hi, &tmap_b_hi, kb * BK, b_row0 + n0, bar_full(stage));
+                        if (!B_SPLIT) tma_load_2d(sb_lo, &tmap_b_lo, kb * BK, b_row0 + n0, bar_full(stage));
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -247,8 +285,11 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int64_t m0 = static_cast<int64_t>(w / args.n_tiles_n) * kBM;
-            const int n0 = (w % args.n_tiles_n) * BN;
+            GroupedTile gt;
+            ts_decode<GROUPED>(w, args, tile_prefix, gt);
+            const int64_t m0 = gt.m0;
+            const int n0 = gt.n0;
+            const bool partial = GROUPED && gt.rows < kBM;      // last tile of a segment: rows beyond it belong to the next one
             bar_wait(bar_tfull(acc), acc_phase);
             tc_fence_after();
             // TMEM -> registers -> swizzled smem box -> TMA store: every global write is a full 128-byte
@@ -269,6 +310,18 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (args.relu) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.0f));
+                }
+                if (partial) {
+                    // row-masked direct stores (a thread owns one row of the 32 x 32 box)
+                    const int row = q * 32 + lane;
+                    if (row < gt.rows) {
+                        float* dst = args.c + (m0 + row) * args.ldc + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    }
+                    continue;
                 }
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this box's previous store has read it
                 __syncwarp();
@@ -293,11 +346,11 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <bool B_MN, bool B_SPLIT>
+template <bool B_MN, bool B_SPLIT, bool GROUPED = false>
 static int launch_gemm_ts(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tbh, const CUtensorMap& tbl,
                           const CUtensorMap& tc, const CUtensorMap& tc2, const GemmArgs& args, cudaStream_t stream) {
     constexpr size_t smem = kTsStages * (kBM * 32 * 4 + 2 * kTsBN * 32 * 4) + 4 * 2 * 4096 + 256 + 1024;
-    auto kfn = gemm_tf32x3_ts_kernel<B_MN, B_SPLIT>;
+    auto kfn = gemm_tf32x3_ts_kernel<B_MN, B_SPLIT, GROUPED>;
     B200MP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int n_work = args.n_tiles_m * args.n_tiles_n;
     const int grid = n_work < num_sms() ? n_work : num_sms();

@@ -290,7 +290,65 @@ def _mm_tn(a: Tensor, b: Tensor) -> Tensor:
     return a.t() @ b
 
 
+def _grouped(a: Tensor, ptr: Tensor, w_hi: Tensor, w_lo: Tensor, b_layout: int, n_out: int) -> Tensor:
+    m, k = a.shape
+    c = torch.empty((m, n_out), dtype=torch.float32, device=a.device)
+    ops._timed("segment_matmul_tf32x3", 1, lib().b200mp_segment_matmul_tf32x3, a.data_ptr(), ptr.data_ptr(), ptr.numel() - 1,
+               w_hi.data_ptr(), w_lo.data_ptr(), int(b_layout), c.data_ptr(), m, k, n_out, ops._stream())
+    return c
+
+
+def _grouped_ok(inputs: Tensor, other: Tensor) -> bool:
+    R, k, n = other.shape
+    return (_BACKEND == "tf32x3" and inputs.is_cuda and inputs.dtype == torch.float32 and other.dtype == torch.float32
+            and inputs.size(0) > 0 and k % 32 == 0 and n % 128 == 0 and R <= 1024 and inputs.size(0) < 2**31)
+
+
 class _SegmentMatmul(torch.autograd.Function):
+    """Forward and the input gradient are ONE persistent launch each of the grouped tcgen05 kernel (ptr stays on the
+    device); the weight gradient (a reduction over each segment's rows) runs the split-K kernel per segment and reads
+    the R + 1 segment bounds to the host once, in the backward only."""
+
+    @staticmethod
+    def forward(ctx, inputs: Tensor, ptr: Tensor, other: Tensor):
+        inputs = inputs.contiguous()
+        ptr64 = ptr.to(torch.int64).contiguous()
+        w_hi, w_lo = split_tf32(other)
+        ctx.save_for_backward(inputs, ptr64, w_hi, w_lo)
+        return _grouped(inputs, ptr64, w_hi, w_lo, 1, other.size(2))
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        inputs, ptr64, w_hi, w_lo = ctx.saved_tensors
+        g = g.contiguous()
+        R, k, n = w_hi.shape
+        gi = go = None
+        if ctx.needs_input_grad[0]:
+            if n % 32 == 0 and k % 128 == 0:
+                gi = _grouped(g, ptr64, w_hi, w_lo, 0, k)                 # g[seg] . w[r]^T
+            else:
+                gi = torch.empty_like(inputs)
+        bounds = None
+        if ctx.needs_input_grad[2] or (gi is not None and not (n % 32 == 0 and k % 128 == 0)):
+            bounds = ptr64.tolist()
+        if ctx.needs_input_grad[0] and not (n % 32 == 0 and k % 128 == 0):
+            w = w_hi + w_lo
+            for r in range(R):
+                s, e = bounds[r], bounds[r + 1]
+                if e > s:
+                    gi[s:e] = g[s:e] @ w[r].t()
+        if ctx.needs_input_grad[2]:
+            go = torch.zeros((R, k, n), dtype=torch.float32, device=g.device)
+            for r in range(R):
+                s, e = bounds[r], bounds[r + 1]
+                if e > s:
+                    go[r] = _mm_tn(inputs[s:e], g[s:e])
+        return gi, None, go
+
+
+class _SegmentMatmulLoop(torch.autograd.Function):
+    """Shapes off the grouped kernel's grid: one product per segment (library GEMM or the single-segment kernels)."""
+
     @staticmethod
     def forward(ctx, inputs: Tensor, other: Tensor, bounds: tuple):
         out = torch.empty((inputs.size(0), other.size(2)), dtype=inputs.dtype, device=inputs.device)
@@ -322,15 +380,17 @@ class _SegmentMatmul(torch.autograd.Function):
 
 def segment_matmul(inputs: Tensor, ptr: Tensor, other: Tensor) -> Tensor:
     """pyg_lib.ops.segment_matmul (nn/dense/linear.py:248-255, nn/conv/rgcn_conv.py:288):
-    out[ptr[r]:ptr[r+1]] = inputs[ptr[r]:ptr[r+1]] @ other[r], other: [R, K, N].  The R products run on the
-    3xTF32 tcgen05 GEMMs (fp32-accurate) when K % 32 == 0 and N is a supported width, else a library GEMM.
-    The segment bounds are read to the host once (the reference's own implementation reads `ptr` on the host too)."""
+    out[ptr[r]:ptr[r+1]] = inputs[ptr[r]:ptr[r+1]] @ other[r], other: [R, K, N] -- ONE persistent launch of the grouped
+    3xTF32 tcgen05 kernel (fp32-accurate; `ptr` is never read on the host) when K % 32 == 0 and N % 128 == 0, else one
+    product per segment."""
     if not inputs.is_cuda:
         raise RuntimeError("pytorch_geometric_b200 ops run on CUDA tensors only (no CPU fallback)")
     if other.dim() != 3 or inputs.dim() != 2 or inputs.size(1) != other.size(1) or ptr.numel() != other.size(0) + 1:
         raise ValueError("segment_matmul expects inputs [M, K], ptr [R + 1], other [R, K, N]")
+    if _grouped_ok(inputs, other):
+        return _SegmentMatmul.apply(inputs, ptr, other)
     bounds = tuple(int(v) for v in ptr.tolist())
-    return _SegmentMatmul.apply(inputs, other, bounds)
+    return _SegmentMatmulLoop.apply(inputs, other, bounds)
 
 
 def grouped_matmul(inputs, others, biases=None):

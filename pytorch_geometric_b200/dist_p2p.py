@@ -38,51 +38,39 @@ def symmetric_empty(shape, dtype, device, group=None):
     return t, hdl
 
 
-class PeerShardedGCNGraph:
-    """One rank's slice of a gcn_norm'ed graph with GLOBAL column ids:
-      g_fwd: rows = owned destinations, cols = global source ids        (forward gather of x W^T rows)
-      g_bwd: rows = owned sources,      cols = global destination ids   (backward gather of grad rows)
-    plus the symmetric buffers the two gathers read."""
+class PeerShardedGraph:
+    """One rank's slice of a weighted aggregation  out[r] = sum_e w_e x[src_e]  over destination ROWS owned by this rank
+    (one row per node, or R virtual rows per node for a relational graph), with GLOBAL source ids:
+      g_fwd: rows = owned destination rows, cols = global source ids            (forward gather of the x rows)
+      g_bwd: rows = owned sources,          cols = global destination row ids   (backward gather of grad rows)
+    plus the symmetric buffers the two gathers read: `x` [n_local, feat] and `gout` [n_rows_local, feat]."""
 
-    def __init__(self, g_fwd: CSRGraph, g_bwd: CSRGraph, lo: int, n_local: int, n_total: int, feat: int, group):
+    def __init__(self, g_fwd: CSRGraph, g_bwd: CSRGraph, lo: int, n_local: int, n_total: int, n_rows_local: int, feat: int, group):
         self.g_fwd, self.g_bwd = g_fwd, g_bwd
         self.graph = g_fwd
-        self.lo, self.n_local, self.n_total, self.group = lo, n_local, n_total, group
+        self.lo, self.n_local, self.n_total, self.n_rows_local, self.group = lo, n_local, n_total, n_rows_local, group
         self.world = dist.get_world_size(group)
         self.num_edges = g_fwd.num_edges
         dev = g_fwd.device
         self.xw, self.h_xw = symmetric_empty((n_local, feat), torch.float32, dev, group)
-        self.gout, self.h_gout = symmetric_empty((n_local, feat), torch.float32, dev, group)
-        self._chan = 0
+        self.gout, self.h_gout = symmetric_empty((n_rows_local, feat), torch.float32, dev, group)
 
     def barrier(self) -> None:
         """Stream-ordered barrier across the ranks (on the current stream)."""
         self.h_xw.barrier(channel=0)
 
     @classmethod
-    def build(cls, edge_index_global: Tensor, lo: int, n_local: int, n_total: int, feat: int, group=None,
-              add_self_loops: bool = True):
-        from .dist import shard_self_loops
+    def build_weighted(cls, src_global: Tensor, row_local: Tensor, w: Tensor, lo: int, n_local: int, n_total: int,
+                       n_rows_local: int, feat: int, group=None):
+        """src_global [E]: global source ids of this rank's in-edges; row_local [E]: destination row in
+        [0, n_rows_local); w [E]: the edge weights (computed by the destination's owner: gcn_norm, 1 / in-degree, ...)."""
         group = group if group is not None else dist.group.WORLD
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        dev = edge_index_global.device
-        src, dst = edge_index_global[0], edge_index_global[1]          # dst in [lo, lo + n_local)
-        if add_self_loops:
-            src, dst = shard_self_loops(src, dst, lo, n_local)
-        dst_l = dst - lo
-        # gcn_norm: in-degrees are local; dinv of every node by one all_gather (4 B per node)
-        deg = ops.degree(dst_l, n_local).to(torch.float32)
-        dinv = deg.pow(-0.5)
-        dinv.masked_fill_(dinv == float("inf"), 0.0)
-        dinv_all = torch.empty(n_total, dtype=torch.float32, device=dev)
-        if world > 1:
-            dist.all_gather_into_tensor(dinv_all, dinv, group=group)
-        else:
-            dinv_all.copy_(dinv)
-        w = ops.gather_rows(dinv_all.view(-1, 1), src).view(-1) * ops.gather_rows(dinv.view(-1, 1), dst_l).view(-1)
-        g_fwd = CSRGraph(src, dst_l, n_total, n_local, w)
-        # mirror structure: send every edge to the owner of its SOURCE
-        owner = torch.div(src, n_local, rounding_mode="floor")
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        dev = src_global.device
+        g_fwd = CSRGraph(src_global, row_local, n_total, n_rows_local, w)
+        # mirror structure: send every edge (source, GLOBAL destination row, weight) to the owner of its SOURCE
+        owner = torch.div(src_global, n_local, rounding_mode="floor")
         order = torch.sort(owner, stable=True)[1]
         counts = torch.bincount(owner, minlength=world)
         send_counts = counts.tolist()
@@ -103,10 +91,60 @@ class PeerShardedGCNGraph:
                 out.copy_(inp)
             return out
 
-        src_b, dst_b, w_b = exchange(src), exchange(dst), exchange(w)
+        row_global = row_local.to(torch.int64) + rank * n_rows_local
+        src_b, row_b, w_b = exchange(src_global), exchange(row_global), exchange(w)
         assert n_recv == 0 or (int(src_b.min()) >= lo and int(src_b.max()) < lo + n_local)
-        g_bwd = CSRGraph(dst_b, src_b - lo, n_total, n_local, w_b)      # rows = owned sources, cols = global dst ids
-        return cls(g_fwd, g_bwd, lo, n_local, n_total, feat, group)
+        g_bwd = CSRGraph(row_b, src_b - lo, world * n_rows_local, n_local, w_b)   # rows = owned sources, cols = global dst rows
+        return cls(g_fwd, g_bwd, lo, n_local, n_total, n_rows_local, feat, group)
+
+
+class PeerShardedGCNGraph(PeerShardedGraph):
+    """The gcn_norm'ed graph (D^-1/2 (A + I) D^-1/2) sharded by node range."""
+
+    @classmethod
+    def build(cls, edge_index_global: Tensor, lo: int, n_local: int, n_total: int, feat: int, group=None,
+              add_self_loops: bool = True):
+        from .dist import shard_self_loops
+        group = group if group is not None else dist.group.WORLD
+        world = dist.get_world_size(group)
+        dev = edge_index_global.device
+        src, dst = edge_index_global[0], edge_index_global[1]          # dst in [lo, lo + n_local)
+        if add_self_loops:
+            src, dst = shard_self_loops(src, dst, lo, n_local)
+        dst_l = dst - lo
+        # gcn_norm: in-degrees are local; dinv of every node by one all_gather (4 B per node)
+        deg = ops.degree(dst_l, n_local).to(torch.float32)
+        dinv = deg.pow(-0.5)
+        dinv.masked_fill_(dinv == float("inf"), 0.0)
+        dinv_all = torch.empty(n_total, dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.all_gather_into_tensor(dinv_all, dinv, group=group)
+        else:
+            dinv_all.copy_(dinv)
+        w = ops.gather_rows(dinv_all.view(-1, 1), src).view(-1) * ops.gather_rows(dinv.view(-1, 1), dst_l).view(-1)
+        return cls.build_weighted(src, dst_l, w, lo, n_local, n_total, n_local, feat, group)
+
+
+class PeerShardedRelGraph(PeerShardedGraph):
+    """The relational graph of RGCNConv (virtual destination row dst * R + type, per-relation mean = weight
+    1 / in-degree of the virtual row), sharded by node range: every rank owns R rows per owned node."""
+
+    @classmethod
+    def build(cls, edge_index_global: Tensor, edge_type: Tensor, num_relations: int, lo: int, n_local: int, n_total: int,
+              feat: int, group=None, aggr: str = "mean"):
+        src, dst = edge_index_global[0], edge_index_global[1]
+        row = (dst - lo).to(torch.int64) * num_relations + edge_type.to(torch.int64)
+        n_rows = n_local * num_relations
+        if aggr == "mean":
+            cnt = ops.degree(row, n_rows).clamp(min=1).to(torch.float32)
+            w = ops.gather_rows((1.0 / cnt).view(-1, 1), row).view(-1)
+        elif aggr in ("sum", "add"):
+            w = torch.ones(row.numel(), dtype=torch.float32, device=src.device)
+        else:
+            raise NotImplementedError("sharded RGCN: aggr must be mean or sum")
+        shard = cls.build_weighted(src, row, w, lo, n_local, n_total, n_rows, feat, group)
+        shard.num_relations = num_relations
+        return shard
 
 
 class _LinearInto(torch.autograd.Function):
@@ -162,16 +200,49 @@ class _PeerAggregate(torch.autograd.Function):
         g = shard.g_bwd
         gx = gb = None
         if grad_out.data_ptr() != shard.gout.data_ptr():
-            shard.gout.copy_(grad_out)           # upstream did not produce the gradient in the symmetric buffer
+            shard.gout.copy_(grad_out.reshape(shard.gout.shape))   # upstream did not produce the gradient in the symmetric buffer
         grad_sym = shard.gout
         shard.barrier()                          # every rank's gradient rows are in place before anyone gathers them
         if ctx.needs_input_grad[0]:
             gx = ops.spmm_csr(g.rowptr, g.col, g.val, grad_sym, g.num_dst, "sum", g.plan,
-                              peer_ptrs=shard.h_gout.buffer_ptrs_dev, peer_rows=shard.n_local)
+                              peer_ptrs=shard.h_gout.buffer_ptrs_dev, peer_rows=shard.n_rows_local)
         if ctx.has_bias and ctx.needs_input_grad[1]:
             gb = grad_sym.sum(0, dtype=torch.float32)
         shard.barrier()                          # peers are done reading my gradient rows
         return gx, gb, None
+
+
+def peer_aggregate(x_local: Tensor, shard: PeerShardedGraph, bias: Optional[Tensor] = None) -> Tensor:
+    """out[r] = sum_e w_e x[src_e] (+ bias) for this rank's destination rows, sources anywhere: x_local is copied into
+    the symmetric buffer unless it already lives there."""
+    if x_local.data_ptr() != shard.xw.data_ptr():
+        x_local = _CopyInto.apply(x_local, shard.xw.detach())
+    return _PeerAggregate.apply(x_local, bias, shard)
+
+
+class _CopyInto(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, out: Tensor):
+        out.copy_(x)
+        ctx.mark_dirty(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        return g, None
+
+
+def peer_sharded_rgcn_conv(weight: Tensor, root: Optional[Tensor], bias: Optional[Tensor], x_local: Tensor,
+                           shard: "PeerShardedRelGraph") -> Tensor:
+    """RGCNConv.forward on one shard (rgcn_conv.py:257-280): the per-relation aggregation gathers remote source rows
+    over NVLink inside the kernel; the K = R*F (+ root) product is local."""
+    R, Fi, Fo = weight.shape
+    h = peer_aggregate(x_local, shard).view(shard.n_local, R * Fi)
+    w = weight.reshape(R * Fi, Fo)
+    if root is not None:
+        return dense.matmul_pair(h, w, x_local, root, bias)
+    out = dense.matmul(h, w)
+    return out if bias is None else out + bias
 
 
 def peer_sharded_gcn_conv(conv, x_local: Tensor, shard: PeerShardedGCNGraph) -> Tensor:

@@ -69,7 +69,7 @@ class CSRGraph:
     @classmethod
     def from_csr(cls, rowptr: Tensor, col: Tensor, num_src: int, edge_weight: Optional[Tensor] = None,
                  transposed: Optional[tuple] = None, chunk: int = DEFAULT_CHUNK,
-                 idx_dtype: Optional[torch.dtype] = None) -> "CSRGraph":
+                 idx_dtype: Optional[torch.dtype] = None, bounded_degree: bool = False) -> "CSRGraph":
         """Adopts an EXISTING destination-sorted CSR -- an `EdgeIndex`'s cached `(indptr, other index)`
         (edge_index.py:626-696), a `torch.sparse_csr` tensor's `(crow_indices, col_indices)`, a loader's `ptr` --
         without sorting anything: the caller's edge order IS the CSR order (`perm` = identity, stored as None).
@@ -90,7 +90,9 @@ class CSRGraph:
         g.perm = None
         g._src, g._dst = g.col, None                          # _dst = ptr2index(rowptr), materialised on demand
         g.val = None if edge_weight is None else edge_weight.detach().float().contiguous()
-        g.plan = ops.LongRowPlan(g.rowptr, g.chunk)
+        # bounded_degree: the caller guarantees short rows (sampled mini-batches): no long-row count, no host sync
+        g._bounded = bool(bounded_degree)
+        g.plan = ops.LongRowPlan.empty(g.chunk) if bounded_degree else ops.LongRowPlan(g.rowptr, g.chunk)
         g._t_built = False
         g.perm_t = g.rowptr_t = g.col_t = g.val_t = g.plan_t = None
         g._mean_val_t = g._inv_perm = g._inv_perm_t = g._dst_csr = g._t2csr = None
@@ -113,10 +115,37 @@ class CSRGraph:
             self._dst = self.dst_csr
         _, self.perm_t, self.rowptr_t = ops.sort_by_key(self._src, self.num_src, want_sorted=False)
         self.col_t = ops.permute(self._dst, self.perm_t)
-        self.plan_t = ops.LongRowPlan(self.rowptr_t, self.chunk)
+        self.plan_t = ops.LongRowPlan(self.rowptr_t, self.chunk)          # (source hubs exist even in sampled batches)
         self._t_built = True
         if self.val is not None:
             self.val_t = self.to_csc_order(self.from_csr_order(self.val))
+
+    def trim(self, num_dst: int, num_src: int, num_edges: int) -> "CSRGraph":
+        """The sub-graph of the first `num_dst` destination rows, `num_src` sources and `num_edges` CSR slots, as
+        VIEWS of this graph's arrays -- `trim_to_layer` (utils/_trim_to_layer.py:20-217) for a destination-sorted
+        sampled subgraph: NeighborLoader emits the hops in BFS order, so the nodes and edges a deeper layer no
+        longer needs are exactly the tails of the node / CSR arrays.  No sort, no edge copy, no host sync.
+        Requires an adopted CSR (caller's edge order == CSR order)."""
+        if self.perm is not None:
+            raise ValueError("trim() needs a graph adopted with from_csr (edge order == CSR order)")
+        if not (0 <= num_dst <= self.num_dst and 0 <= num_src <= self.num_src and 0 <= num_edges <= self.num_edges):
+            raise ValueError("trim(): sizes must not exceed the graph's")
+        g = object.__new__(CSRGraph)
+        g.idx_dtype, g.chunk, g.device = self.idx_dtype, self.chunk, self.device
+        g.num_src, g.num_dst, g.num_edges = int(num_src), int(num_dst), int(num_edges)
+        # rows whose in-edges all lie in the dropped tail (the previous hop's frontier: sources only from now on) must
+        # end at num_edges: one clamp over the [num_dst + 1] row pointers (the edge arrays stay views)
+        g.rowptr = self.rowptr[:num_dst + 1].clamp(max=num_edges)
+        g.col = self.col[:num_edges]
+        g.perm = None
+        g._src, g._dst = g.col, None
+        g.val = None if self.val is None else self.val[:num_edges]
+        g._bounded = getattr(self, "_bounded", False)
+        g.plan = ops.LongRowPlan.empty(g.chunk) if g._bounded else ops.LongRowPlan(g.rowptr, g.chunk)
+        g._t_built = False
+        g.perm_t = g.rowptr_t = g.col_t = g.val_t = g.plan_t = None
+        g._mean_val_t = g._inv_perm = g._inv_perm_t = g._dst_csr = g._t2csr = None
+        return g
 
     # per-edge tensor permutations (1-D fp32 / int tensors)
     def to_csr_order(self, per_edge: Tensor) -> Tensor:

@@ -610,3 +610,39 @@ class TransformerConv(torch.nn.Module):
 
     def __repr__(self) -> str:
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})"
+
+
+class HeteroLinear(torch.nn.Module):
+    """Mirror of torch_geometric.nn.HeteroLinear (nn/dense/linear.py:174-340): x_k W_k + b_k per type k.  The per-type
+    products are ONE launch of the grouped tcgen05 kernel (dense.segment_matmul); unsorted type vectors are sorted
+    with the engine's stable radix sort and the result is un-permuted, as the reference does."""
+
+    def __init__(self, in_channels: int, out_channels: int, num_types: int, is_sorted: bool = False, bias: bool = True, **kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels, self.num_types, self.is_sorted = in_channels, out_channels, num_types, is_sorted
+        self.weight = torch.nn.Parameter(torch.empty(num_types, in_channels, out_channels))
+        self.bias = torch.nn.Parameter(torch.zeros(num_types, out_channels)) if bias else None
+        bound = 1.0 / math.sqrt(in_channels)                          # reset_weight_ (linear.py:42-60): kaiming_uniform(a=sqrt(5))
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound)
+            if self.bias is not None:
+                self.bias.uniform_(-bound, bound)
+
+    def forward(self, x: Tensor, type_vec: Tensor) -> Tensor:
+        perm = None
+        if not self.is_sorted:
+            type_vec, perm = U.index_sort(type_vec, self.num_types - 1)
+            x = ops.gather_rows(x, perm) if x.dtype in (torch.float32, torch.bfloat16) and not x.requires_grad else x[perm]
+        ptr = ops.index2ptr(type_vec, self.num_types)
+        out = dense.segment_matmul(x, ptr, self.weight)
+        if self.bias is not None:
+            out = out + self.bias[type_vec.long()]
+        if perm is not None:
+            out_unsorted = torch.empty_like(out)
+            out_unsorted[perm] = out
+            out = out_unsorted
+        return out
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, num_types={self.num_types}, "
+                f"bias={self.bias is not None})")

@@ -238,6 +238,17 @@ class LongRowPlan:
                                              _p(self.chunk_ptr), _p(ws), ws.numel(), it, _stream()),
                   "csr_plan_fill")
 
+    @classmethod
+    def empty(cls, chunk: int = 512) -> "LongRowPlan":
+        """A plan without long rows, built WITHOUT the device->host count: always correct (a row above `chunk` edges
+        is then simply walked by one lane group), meant for graphs whose degrees are bounded by construction
+        (neighbour-sampled mini-batches: degree <= fan-out)."""
+        p = object.__new__(cls)
+        p.n_long = p.n_chunks = 0
+        p.chunk = int(chunk)
+        p.long_rows = p.chunk_ptr = p._partials = None
+        return p
+
     def partials(self, feat: int, device) -> Optional[Tensor]:
         if not self.n_long:
             return None

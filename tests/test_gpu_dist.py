@@ -62,6 +62,41 @@ def _run_rank(rank, world, port, n_total, n_edges, q, mode="nccl"):
         # sharded
         mine = (ei[1] >= lo) & (ei[1] < lo + n_local)
         xl = x[lo:lo + n_local].to(dev).requires_grad_()
+        if mode == "p2p_rgcn":
+            # config 5's layer sharded over the ranks: per-relation mean gathered over NVLink, local K = (R+1) F product
+            from pytorch_geometric_b200 import dist_p2p
+            from pytorch_geometric_b200.graph import cached_graph
+            from pytorch_geometric_b200.nn import conv as C
+            g = torch.Generator().manual_seed(21)
+            R, F = 3, 128
+            et = torch.randint(0, R, (ei.size(1), ), generator=g)
+            xr = torch.randn(n_total, F, generator=g)
+            Wr = (torch.randn(R, F, F, generator=g) / 11).to(dev).requires_grad_()
+            root = (torch.randn(F, F, generator=g) / 11).to(dev).requires_grad_()
+            bb = (torch.randn(F, generator=g) * 0.1).to(dev).requires_grad_()
+            gr = torch.randn(n_total, F, generator=g)
+            xg = xr.to(dev).requires_grad_()
+            graph = cached_graph(ei.to(dev), n_total, n_total * R, edge_type=et.to(dev), num_relations=R)
+            ref = C.rgcn_conv(xg, graph, Wr, root, bb, "mean")
+            ref.backward(gr.to(dev))
+            ref_gx, ref_gw, ref_groot = xg.grad.clone(), Wr.grad.clone(), root.grad.clone()
+            Wr.grad = root.grad = bb.grad = None
+            shard = dist_p2p.PeerShardedRelGraph.build(ei[:, mine].to(dev), et[mine].to(dev), R, lo, n_local, n_total, F)
+            xl2 = xr[lo:lo + n_local].to(dev).requires_grad_()
+            for _ in range(2):
+                xl2.grad = None
+                Wr.grad = root.grad = bb.grad = None
+                out = dist_p2p.peer_sharded_rgcn_conv(Wr, root, bb, xl2, shard)
+                out.backward(gr[lo:lo + n_local].to(dev))
+            gw2, gr2 = Wr.grad.clone(), root.grad.clone()
+            dist.all_reduce(gw2)
+            dist.all_reduce(gr2)
+            torch.testing.assert_close(out, ref[lo:lo + n_local], rtol=1e-4, atol=1e-4)
+            torch.testing.assert_close(xl2.grad, ref_gx[lo:lo + n_local], rtol=1e-4, atol=1e-4)
+            torch.testing.assert_close(gw2, ref_gw, rtol=1e-3, atol=1e-3)
+            torch.testing.assert_close(gr2, ref_groot, rtol=1e-3, atol=1e-3)
+            q.put((rank, "ok"))
+            return
         if mode == "p2p_stack":
             # two stacked layers SHARING one shard (one symmetric x W^T buffer), forward-only: the second layer's
             # dense transform overwrites the buffer the first layer's gather read -- legal only because of the
@@ -138,3 +173,9 @@ def test_peer_memory_gcn_conv_two_ranks_equals_unsharded():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_peer_memory_two_stacked_layers_share_one_shard_forward_only():
     _launch(2, "p2p_stack")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_peer_memory_rgcn_conv_two_ranks_equals_unsharded():
+    """BASELINE config 5 (RGCNConv, 2 x B200): the reduce-agnostic peer-sharded aggregate under the relational layer."""
+    _launch(2, "p2p_rgcn")

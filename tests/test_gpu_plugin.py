@@ -243,6 +243,9 @@ def test_subclass_layers_match_the_reference_layers(tg, plugin, name, args, kw):
     _close(xg.grad, xc.grad, tol=2e-4, what=name + " grad_x")
     for (n, pg), (_, pc) in zip(ours.named_parameters(), ref.named_parameters()):
         if pc.grad is not None:
+            if n == "lin_key.bias":       # softmax is shift invariant: this gradient is exactly 0 up to rounding noise
+                assert pg.grad.abs().max().item() < 1e-4 and pc.grad.abs().max().item() < 1e-4
+                continue
             _close(pg.grad, pc.grad, tol=5e-4, what=f"{name} grad {n}")
 
 
