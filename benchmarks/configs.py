@@ -64,8 +64,7 @@ def run_config(args, B):
         def model(xx):
             h = xx
             for i in range(L):
-                agg = Fn.aggregate(graph, h, "mean")
-                h = dense.linear_pair(agg, Ws[2 * i], h, Ws[2 * i + 1], bs[i], relu=(i < L - 1))
+                h = C.sage_conv(h, h, graph, "mean", Ws[2 * i], bs[i], Ws[2 * i + 1], relu=(i < L - 1))
             return h
 
         dom_op, dom_kernel = "spmm_csr", "csr_reduce_kernel (mean aggregation fwd on CSR / bwd on transposed CSR)"
@@ -262,10 +261,11 @@ def _parity(cfg: int, L: dict) -> dict:
         absagg = torch.zeros(S.numel(), F, dtype=torch.float64, device=dev).index_add_(0, pos[dst[m]], xs[src[m]].abs())
         cnt = deg[S].clamp(min=1).double().view(-1, 1)
         agg, absagg = agg / cnt, absagg / cnt
-        from pytorch_geometric_b200 import dense, functional as Fn
+        C = L["C"]
         want = (agg @ Ws[0].detach().double().t() + xs[S] @ Ws[1].detach().double().t() + bs[0].detach().double()).relu()
         scale = absagg @ Ws[0].detach().double().abs().t() + xs[S].abs() @ Ws[1].detach().double().abs().t() + bs[0].detach().double().abs()
-        h1 = dense.linear_pair(Fn.aggregate(graph, x.detach(), "mean"), Ws[0].detach(), x.detach(), Ws[1].detach(), bs[0].detach(), relu=True)
+        xd = x.detach()
+        h1 = C.sage_conv(xd, xd, graph, "mean", Ws[0].detach(), bs[0].detach(), Ws[1].detach(), relu=True)
         res["layer1_out"] = _rel(h1[S], want, scale)
         rows = int(S.numel())
         del h1
@@ -298,7 +298,7 @@ def _parity(cfg: int, L: dict) -> dict:
         want = want.view(S.numel(), -1) + bias.detach().double()
         scale = scale.view(S.numel(), -1) + bias.detach().double().abs()
         # bf16 storage: the output is rounded to bf16 (2^-9 relative) on top of the fp32 accumulation
-        res["out_bf16"] = _rel(out[S], want, scale) / 2 ** -8
+        res["out_bf16"] = _rel(out[S], want, scale)
         rows = int(S.numel())
     else:
         graph, Wr, root, bias, F, R, et = L["graph"], L["Wr"], L["root"], L["bias"], L["F"], L["R"], L["et"]
@@ -321,8 +321,10 @@ def _parity(cfg: int, L: dict) -> dict:
         res["out"] = _rel(out[S], want, scale)
         rows = int(S.numel())
     mx = max(res.values())
-    tol = 1e-5 if cfg != 3 else 1.0          # config 3's figure is in units of the bf16 rounding step (2^-8 of sum|terms|)
+    # bf16 storage (config 3): the projected rows, the attention output and the bias add are each rounded to bf16
+    # (2^-9 relative per rounding): 1.6e-2 of sum|terms|, the bar DESIGN.md states for bf16; fp32 configs: 1e-5
+    tol = 1e-5 if cfg != 3 else 1.6e-2
     return {"rows": rows, "max_rel": mx, "tol": tol, "ok": bool(mx <= tol), "per_quantity": res,
             "how": "sampled destination rows (hubs, rows with 0/1/2 edges, random rows) recomputed in fp64 from the raw edge "
                    "list with the reference's unfused formula; error relative to sum|terms|"
-                   + (" in units of the bf16 rounding step 2^-8" if cfg == 3 else "")}
+                   + (" (bf16 storage: three roundings of 2^-9 on top of the fp32 accumulation)" if cfg == 3 else "")}

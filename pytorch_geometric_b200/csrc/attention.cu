@@ -70,7 +70,7 @@ __device__ __forceinline__ void merge_ms(float m1, float m2, float& M, float& c1
 
 // ------------------------------------------------------------------------------------------------ forward
 template <typename T, typename I, int G, int VPL, int MODE>
-__global__ void __launch_bounds__(kAttnT)
+__global__ void __launch_bounds__(kAttnT, VPL == 1 ? 8 : 5)       // <= 64 registers: 32 warps / SM (latency-bound gather)
 attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArgs a, T* __restrict__ out,
                 float* __restrict__ row_max, float* __restrict__ row_den, int64_t n_rows, LongRowPlan plan,
                 float* __restrict__ part_ms) {
@@ -107,68 +107,77 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
         }
     }
 
-    for (int64_t e0 = begin; e0 < end; e0 += S * UNR) {
-        Vec16 vb[UNR][VPL], kb[UNR][VPL];
-        float sc[UNR][VPL];
-        bool ev[UNR];
+    // Column indices are loaded by the whole warp, 32 edges at a time (coalesced, one batch ahead of the row loads so
+    // the index latency is off the critical path) and handed to the lane groups by shuffle.
+    I c_next = (begin + lane < end) ? ldg_idx(col + begin + lane) : I(0);
+    for (int64_t b0 = begin; b0 < end; b0 += 32) {
+        const I c_cur = c_next;
+        const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
+        c_next = (b0 + 32 + lane < end) ? ldg_idx(col + b0 + 32 + lane) : I(0);
+        for (int j0 = 0; j0 < nb; j0 += S * UNR) {
+            Vec16 vb[UNR][VPL], kb[UNR][VPL];
+            float sc[UNR][VPL];
+            bool ev[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int64_t e = e0 + u * S + sub;
-            ev[u] = e < end;
-            if (ev[u]) {
-                const int64_t c = static_cast<int64_t>(ldg_idx(col + e));
+            for (int u = 0; u < UNR; ++u) {
+                const int j = j0 + u * S + sub;
+                ev[u] = j < nb;
+                const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, c_cur, j & 31));
+                if (ev[u]) {
+                    const int64_t e = b0 + j;
 #pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    if (!valid[k]) continue;
-                    const size_t off = static_cast<size_t>(lig + k * G) * 16;
-                    vb[u][k] = ldg_row16(a.v + static_cast<size_t>(c) * a.v_stride + off);
-                    if (MODE == ATTN_DOT) kb[u][k] = ldg_row16(a.k + static_cast<size_t>(c) * a.k_stride + off);
-                    if (MODE == ATTN_GAT) {
-                        sc[u][k] = __ldg(a.s_src + c * a.heads + head[k]);
-                        if (a.s_edge) sc[u][k] += __ldg(a.s_edge + e * a.heads + head[k]);
+                    for (int k = 0; k < VPL; ++k) {
+                        if (!valid[k]) continue;
+                        const size_t off = static_cast<size_t>(lig + k * G) * 16;
+                        vb[u][k] = ldg_row16(a.v + static_cast<size_t>(c) * a.v_stride + off);
+                        if (MODE == ATTN_DOT) kb[u][k] = ldg_row16(a.k + static_cast<size_t>(c) * a.k_stride + off);
+                        if (MODE == ATTN_GAT) {
+                            sc[u][k] = __ldg(a.s_src + c * a.heads + head[k]);
+                            if (a.s_edge) sc[u][k] += __ldg(a.s_edge + e * a.heads + head[k]);
+                        }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            float f[VPL][EPV], l[VPL];
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-                l[k] = 0.0f;
-                if (ev[u] && valid[k]) {
-                    ElemTraits<T>::unpack(vb[u][k], f[k]);
-                    if (MODE == ATTN_GAT) l[k] = leaky_f(sc[u][k] + sd[k], a.slope);
-                    if (MODE == ATTN_GATV2) {
-#pragma unroll
-                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i], a.slope), l[k]);
-                    }
-                    if (MODE == ATTN_DOT) {
-                        float kf[EPV];
-                        ElemTraits<T>::unpack(kb[u][k], kf);
-#pragma unroll
-                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(qv[k][i], kf[i], l[k]);
-                    }
-                }
-            }
-            if (MODE != ATTN_GAT) {
+            for (int u = 0; u < UNR; ++u) {
+                float f[VPL][EPV], l[VPL];
 #pragma unroll
                 for (int k = 0; k < VPL; ++k) {
-                    l[k] = head_sum(l[k], a.lph);                   // executed by the whole warp
-                    if (MODE == ATTN_DOT) l[k] *= a.scale;
+                    l[k] = 0.0f;
+                    if (ev[u] && valid[k]) {
+                        ElemTraits<T>::unpack(vb[u][k], f[k]);
+                        if (MODE == ATTN_GAT) l[k] = leaky_f(sc[u][k] + sd[k], a.slope);
+                        if (MODE == ATTN_GATV2) {
+#pragma unroll
+                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i], a.slope), l[k]);
+                        }
+                        if (MODE == ATTN_DOT) {
+                            float kf[EPV];
+                            ElemTraits<T>::unpack(kb[u][k], kf);
+#pragma unroll
+                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(qv[k][i], kf[i], l[k]);
+                        }
+                    }
                 }
-            }
-            if (ev[u]) {
+                if (MODE != ATTN_GAT) {
 #pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    if (!valid[k]) continue;
-                    const float mn = fmaxf(m[k], l[k]);
-                    const float rs = expf(m[k] - mn);               // 0 on the first edge (m = -inf)
-                    const float p = expf(l[k] - mn);
-                    s[k] = fmaf(s[k], rs, p);
+                    for (int k = 0; k < VPL; ++k) {
+                        l[k] = head_sum(l[k], a.lph);                   // executed by the whole warp
+                        if (MODE == ATTN_DOT) l[k] *= a.scale;
+                    }
+                }
+                if (ev[u]) {
 #pragma unroll
-                    for (int i = 0; i < EPV; ++i) acc[k][i] = fmaf(acc[k][i], rs, p * f[k][i]);
-                    m[k] = mn;
+                    for (int k = 0; k < VPL; ++k) {
+                        if (!valid[k]) continue;
+                        const float mn = fmaxf(m[k], l[k]);
+                        const float rs = expf(m[k] - mn);               // 0 on the first edge (m = -inf)
+                        const float p = expf(l[k] - mn);
+                        s[k] = fmaf(s[k], rs, p);
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) acc[k][i] = fmaf(acc[k][i], rs, p * f[k][i]);
+                        m[k] = mn;
+                    }
                 }
             }
         }
@@ -226,32 +235,61 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
     }
 }
 
-// Merge the chunk states of every hub row: M = max_c m_c; S = sum_c s_c e^{m_c-M}; out = sum_c acc_c e^{m_c-M} / (S + 1e-16)
+// Merge the chunk states of every hub row: M = max_c m_c; S = sum_c s_c e^{m_c-M}; out = sum_c acc_c e^{m_c-M} / (S + 1e-16).
+// One CTA per hub row; the chunks are dealt to blockDim / W thread slices (W = features padded to a power of two), every
+// slice merges its chunks online, the slices are folded through shared memory: the largest hub of the products-shaped
+// graph has 5566 chunks, which a single thread per feature used to walk serially (1.9 ms of an 18 ms forward).
+constexpr int kCombineT = 1024;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCombineT)
 attn_combine_kernel(T* __restrict__ out, float* __restrict__ row_max, float* __restrict__ row_den, int heads, int chan,
-                    LongRowPlan plan, const float* __restrict__ part_ms) {
+                    LongRowPlan plan, const float* __restrict__ part_ms, int W) {
+    __shared__ float sm[3 * kCombineT];
     const int64_t j = blockIdx.x;
     if (j >= plan.n_long) return;
     const int64_t row = plan.long_rows[j];
     const int64_t c0 = plan.chunk_ptr[j], c1 = plan.chunk_ptr[j + 1];
     const int64_t hc = static_cast<int64_t>(heads) * chan;
-    for (int64_t f = threadIdx.x; f < hc; f += blockDim.x) {
-        const int h = static_cast<int>(f / chan);
-        float M = -__builtin_inff();
-        for (int64_t c = c0; c < c1; ++c) M = fmaxf(M, part_ms[(c * heads + h) * 2]);
-        float S = 0.0f, acc = 0.0f;
-        for (int64_t c = c0; c < c1; ++c) {
-            const float sc = expf(part_ms[(c * heads + h) * 2] - M);
-            S = fmaf(part_ms[(c * heads + h) * 2 + 1], sc, S);
-            acc = fmaf(plan.partials[c * hc + f], sc, acc);
+    const int n_slices = kCombineT / W;
+    const int slice = threadIdx.x / W;
+    for (int64_t f0 = 0; f0 < hc; f0 += W) {
+        const int64_t f = f0 + (threadIdx.x % W);
+        const bool fv = f < hc && slice < n_slices;
+        const int h = fv ? static_cast<int>(f / chan) : 0;
+        float M = -__builtin_inff(), S = 0.0f, acc = 0.0f;
+        if (fv) {
+            for (int64_t c = c0 + slice; c < c1; c += n_slices) {
+                const float mc = part_ms[(c * heads + h) * 2], sc = part_ms[(c * heads + h) * 2 + 1];
+                const float Mn = fmaxf(M, mc);
+                const float r0 = (M == -__builtin_inff()) ? 0.0f : expf(M - Mn);
+                const float r1 = (mc == -__builtin_inff()) ? 0.0f : expf(mc - Mn);
+                S = S * r0 + sc * r1;
+                acc = acc * r0 + plan.partials[c * hc + f] * r1;
+                M = Mn;
+            }
         }
-        const float den = S + 1e-16f;
-        out[row * hc + f] = ElemTraits<T>::from_float(acc / den);
-        if (f % chan == 0) {
-            row_max[row * heads + h] = M;
-            row_den[row * heads + h] = den;
+        sm[threadIdx.x] = M;
+        sm[kCombineT + threadIdx.x] = S;
+        sm[2 * kCombineT + threadIdx.x] = acc;
+        __syncthreads();
+        if (fv && slice == 0) {
+            for (int sl = 1; sl < n_slices; ++sl) {
+                const int t = sl * W + (threadIdx.x % W);
+                const float m2 = sm[t], s2 = sm[kCombineT + t], a2 = sm[2 * kCombineT + t];
+                float Mn, r0, r1;
+                merge_ms(M, m2, Mn, r0, r1);
+                S = S * r0 + s2 * r1;
+                acc = acc * r0 + a2 * r1;
+                M = Mn;
+            }
+            const float den = S + 1e-16f;
+            out[row * hc + f] = ElemTraits<T>::from_float(acc / den);
+            if (f % chan == 0) {
+                row_max[row * heads + h] = M;
+                row_den[row * heads + h] = den;
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -319,16 +357,23 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
             for (int k = 0; k < VPL; ++k) D[k] = head_sum(D[k], a.lph);
         }
 
-        for (int64_t e0 = begin; e0 < end; e0 += S * UNR) {
+        I c_next = (begin + lane < end) ? ldg_idx(col + begin + lane) : I(0);
+        for (int64_t b0 = begin; b0 < end; b0 += 32) {
+        const I c_cur = c_next;
+        const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
+        c_next = (b0 + 32 + lane < end) ? ldg_idx(col + b0 + 32 + lane) : I(0);
+        for (int j0 = 0; j0 < nb; j0 += S * UNR) {
+            const int64_t e0 = b0 + j0;
             Vec16 vb[UNR][VPL], kb[UNR][VPL];
             float sc[UNR][VPL];
             bool ev[UNR];
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
-                const int64_t e = e0 + u * S + sub;
-                ev[u] = e < end;
+                const int jj = j0 + u * S + sub;
+                const int64_t e = b0 + jj;
+                ev[u] = jj < nb;
+                const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, c_cur, jj & 31));
                 if (ev[u]) {
-                    const int64_t c = static_cast<int64_t>(ldg_idx(col + e));
 #pragma unroll
                     for (int k = 0; k < VPL; ++k) {
                         if (!valid[k]) continue;
@@ -410,6 +455,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
                 }
             }
         }
+        }
         if (ALPHA_ONLY) continue;
         // sum the lane groups' per-row partial gradients
 #pragma unroll
@@ -475,7 +521,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
 
 // ------------------------------------------------------------------------------------------------ backward, source sweep
 template <typename T, typename I, int G, int VPL, int MODE>
-__global__ void __launch_bounds__(kAttnT)
+__global__ void __launch_bounds__(kAttnT, VPL == 1 ? 8 : 5)
 attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t, const I* __restrict__ t2csr, AttnArgs a,
                     const T* __restrict__ grad_out, const float* __restrict__ pair, T* __restrict__ grad_v,
                     T* __restrict__ grad_k, float* __restrict__ grad_s_src, int64_t n_src, LongRowPlan plan) {
@@ -509,17 +555,30 @@ attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t,
             for (int i = 0; i < EPV; ++i) av[k][i] = __ldg(a.att + v * EPV + i);
         }
     }
-    for (int64_t e0 = begin; e0 < end; e0 += S * UNR) {
+    I d_next = 0, p_next = 0;
+    if (begin + lane < end) {
+        d_next = ldg_idx(col_t + begin + lane);
+        p_next = ldg_idx(t2csr + begin + lane);
+    }
+    for (int64_t b0 = begin; b0 < end; b0 += 32) {
+    const I d_cur = d_next, p_cur = p_next;
+    const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
+    d_next = p_next = 0;
+    if (b0 + 32 + lane < end) {
+        d_next = ldg_idx(col_t + b0 + 32 + lane);
+        p_next = ldg_idx(t2csr + b0 + 32 + lane);
+    }
+    for (int j0 = 0; j0 < nb; j0 += S * UNR) {
         Vec16 gbuf[UNR][VPL], qb[UNR][VPL];
         float2 pr[UNR][VPL];
         bool ev[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const int64_t e = e0 + u * S + sub;
-            ev[u] = e < end;
+            const int jj = j0 + u * S + sub;
+            ev[u] = jj < nb;
+            const int64_t d = static_cast<int64_t>(__shfl_sync(0xffffffffu, d_cur, jj & 31));
+            const int64_t p = static_cast<int64_t>(__shfl_sync(0xffffffffu, p_cur, jj & 31));
             if (ev[u]) {
-                const int64_t d = static_cast<int64_t>(ldg_idx(col_t + e));
-                const int64_t p = static_cast<int64_t>(ldg_idx(t2csr + e));
 #pragma unroll
                 for (int k = 0; k < VPL; ++k) {
                     if (!valid[k]) continue;
@@ -555,6 +614,7 @@ attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t,
                 }
             }
         }
+    }
     }
 #pragma unroll
     for (int o = G; o < 32; o <<= 1) {
@@ -595,22 +655,35 @@ attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t,
     }
 }
 
-// Fold fp32 chunk partials [n_chunks, width] of every long row, in chunk order, into up to two typed row outputs
-// (w0 / w1 elements at row strides s0 / s1 BYTES) and one fp32 output (wf floats per row).
+// Fold fp32 chunk partials [n_chunks, width] of every long row into up to two typed row outputs (w0 / w1 elements at row
+// strides s0 / s1 BYTES) and one fp32 output (wf floats per row).  One CTA per long row, chunks dealt to blockDim / W
+// thread slices and folded in a fixed order through shared memory (deterministic).
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCombineT)
 attn_sum_combine_kernel(LongRowPlan plan, int64_t width, T* __restrict__ o0, int64_t w0, size_t s0, T* __restrict__ o1,
-                        int64_t w1, size_t s1, float* __restrict__ of, int64_t wf) {
+                        int64_t w1, size_t s1, float* __restrict__ of, int64_t wf, int W) {
+    __shared__ float sm[kCombineT];
     const int64_t j = blockIdx.x;
     if (j >= plan.n_long) return;
     const int64_t row = plan.long_rows[j];
     const int64_t c0 = plan.chunk_ptr[j], c1 = plan.chunk_ptr[j + 1];
-    for (int64_t f = threadIdx.x; f < width; f += blockDim.x) {
+    const int n_slices = kCombineT / W;
+    const int slice = threadIdx.x / W;
+    for (int64_t f0 = 0; f0 < width; f0 += W) {
+        const int64_t f = f0 + (threadIdx.x % W);
+        const bool fv = f < width && slice < n_slices;
         float acc = 0.0f;
-        for (int64_t c = c0; c < c1; ++c) acc += plan.partials[c * width + f];
-        if (f < w0) reinterpret_cast<T*>(reinterpret_cast<char*>(o0) + row * s0)[f] = ElemTraits<T>::from_float(acc);
-        else if (f < w0 + w1) reinterpret_cast<T*>(reinterpret_cast<char*>(o1) + row * s1)[f - w0] = ElemTraits<T>::from_float(acc);
-        else of[row * wf + (f - w0 - w1)] = acc;
+        if (fv)
+            for (int64_t c = c0 + slice; c < c1; c += n_slices) acc += plan.partials[c * width + f];
+        sm[threadIdx.x] = acc;
+        __syncthreads();
+        if (fv && slice == 0) {
+            for (int sl = 1; sl < n_slices; ++sl) acc += sm[sl * W + (threadIdx.x % W)];
+            if (f < w0) reinterpret_cast<T*>(reinterpret_cast<char*>(o0) + row * s0)[f] = ElemTraits<T>::from_float(acc);
+            else if (f < w0 + w1) reinterpret_cast<T*>(reinterpret_cast<char*>(o1) + row * s1)[f - w0] = ElemTraits<T>::from_float(acc);
+            else of[row * wf + (f - w0 - w1)] = acc;
+        }
+        __syncthreads();
     }
 }
 
@@ -626,6 +699,11 @@ attn_fold_rows_kernel(const float* __restrict__ part, int64_t n_part, int64_t wi
 
 // ------------------------------------------------------------------------------------------------ host side
 inline bool pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+inline int combine_width(int64_t width) {      // features per slice of the combine kernels: a power of two <= kCombineT
+    int w = 1;
+    while (w < width && w < kCombineT) w <<= 1;
+    return w;
+}
 
 template <typename T>
 bool attn_vec_ok(int64_t heads, int64_t chan, const AttnArgs& a, const void* out) {
@@ -665,7 +743,8 @@ int attn_forward_typed(const void* rowptr_, const void* col_, AttnArgs a, void* 
 #undef ATTN_FWD
     B200MP_LAUNCH_CHECK();
     if (plan.n_long > 0) {
-        attn_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), 256, 0, s>>>(out, row_max, row_den, a.heads, a.chan, plan, part_ms);
+        attn_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), kCombineT, 0, s>>>(out, row_max, row_den, a.heads, a.chan, plan, part_ms,
+                                                                                  combine_width(static_cast<int64_t>(a.heads) * a.chan));
         B200MP_LAUNCH_CHECK();
     }
     if (alpha_out && n_edges > 0) {
@@ -700,9 +779,11 @@ int attn_backward_typed(const void* rowptr_, const void* col_, const void* rowpt
         B200MP_LAUNCH_CHECK();
         if (plan.n_long > 0) {
             if (MODE == ATTN_GAT)
-                attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), 256, 0, s>>>(plan, a.heads, nullptr, 0, 0, nullptr, 0, 0, grad_s_dst, a.heads);
+                attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), kCombineT, 0, s>>>(plan, a.heads, nullptr, 0, 0, nullptr, 0, 0, grad_s_dst, a.heads,
+                                                                                              combine_width(a.heads));
             else
-                attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), 256, 0, s>>>(plan, hc, static_cast<T*>(grad_q), hc, static_cast<size_t>(hc) * sizeof(T), nullptr, 0, 0, nullptr, 0);
+                attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan.n_long), kCombineT, 0, s>>>(plan, hc, static_cast<T*>(grad_q), hc, static_cast<size_t>(hc) * sizeof(T), nullptr, 0, 0, nullptr, 0,
+                                                                                              combine_width(hc));
             B200MP_LAUNCH_CHECK();
         }
         if (MODE == ATTN_GATV2) {
@@ -719,8 +800,9 @@ int attn_backward_typed(const void* rowptr_, const void* col_, const void* rowpt
         B200MP_LAUNCH_CHECK();
         if (plan_t.n_long > 0) {
             const int64_t w1 = MODE == ATTN_DOT ? hc : 0, wf = MODE == ATTN_GAT ? a.heads : 0;
-            attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan_t.n_long), 256, 0, s>>>(
-                plan_t, hc + w1 + wf, static_cast<T*>(grad_v), hc, a.v_stride, static_cast<T*>(grad_k), w1, a.k_stride, grad_s_src, wf);
+            attn_sum_combine_kernel<T><<<static_cast<unsigned>(plan_t.n_long), kCombineT, 0, s>>>(
+                plan_t, hc + w1 + wf, static_cast<T*>(grad_v), hc, a.v_stride, static_cast<T*>(grad_k), w1, a.k_stride, grad_s_src, wf,
+                combine_width(hc + w1 + wf));
             B200MP_LAUNCH_CHECK();
         }
     }

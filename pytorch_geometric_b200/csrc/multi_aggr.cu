@@ -387,7 +387,7 @@ int multi_prep_typed(const void* rowptr, MultiPrep p, int64_t n_rows, int64_t fe
     return B200MP_OK;
 }
 
-// fp32 vector form of the backward: a lane group per item, 16-byte loads of the (up to six)
+// fp32 vector form of the backward: a lane group per item, 16-byte loads of the (four + two conditional)
 // per-destination rows, two destinations in flight.
 template <typename I, int G, bool SEGMENT>
 __global__ void __launch_bounds__(128, 6)
@@ -405,32 +405,41 @@ multi_aggr_backward_vec_kernel(const I* __restrict__ ptr, const I* __restrict__ 
         float xv[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
         ElemTraits<float>::unpack(ldg_stream16(reinterpret_cast<const char*>(x) + static_cast<size_t>(j) * row_bytes + voff), xv);
         for (int64_t e = begin; e < end; e += UNR) {
-            Vec16 b[UNR][6];
+            // Four rows per destination are always read (additive term, multiplier of x, forward min, forward max);
+            // the two tie-normalised gradient rows (g_min / ties, g_max / ties) only by the lanes whose x equals the
+            // extremum -- on a hub destination that is ~1 edge in deg per feature, so the sweep moves ~4 rows per edge
+            // instead of 6 (the dependent load is rare; on degree-1 rows it always happens and costs what it did).
+            Vec16 b[UNR][4];
+            size_t offs[UNR];
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 if (e + u < end) {
                     const size_t off = static_cast<size_t>(idx[e + u]) * row_bytes + voff;
+                    offs[u] = off;
                     if (g.a) b[u][0] = ldg_row16(reinterpret_cast<const char*>(g.a) + off);
                     if (g.b) b[u][1] = ldg_row16(reinterpret_cast<const char*>(g.b) + off);
-                    if (g.mn) {
-                        b[u][2] = ldg_row16(static_cast<const char*>(g.mn) + off);
-                        b[u][3] = ldg_row16(reinterpret_cast<const char*>(g.gmin) + off);
-                    }
-                    if (g.mx) {
-                        b[u][4] = ldg_row16(static_cast<const char*>(g.mx) + off);
-                        b[u][5] = ldg_row16(reinterpret_cast<const char*>(g.gmax) + off);
-                    }
+                    if (g.mn) b[u][2] = ldg_row16(static_cast<const char*>(g.mn) + off);
+                    if (g.mx) b[u][3] = ldg_row16(static_cast<const char*>(g.mx) + off);
                 }
             }
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 if (e + u < end) {
+                    bool hit_mn = false, hit_mx = false;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        hit_mn = hit_mn || (g.mn && xv[i] == __uint_as_float(b[u][2].w[i]));
+                        hit_mx = hit_mx || (g.mx && xv[i] == __uint_as_float(b[u][3].w[i]));
+                    }
+                    Vec16 gmn, gmx;
+                    if (hit_mn) gmn = ldg_row16(reinterpret_cast<const char*>(g.gmin) + offs[u]);
+                    if (hit_mx) gmx = ldg_row16(reinterpret_cast<const char*>(g.gmax) + offs[u]);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float t = g.a ? __uint_as_float(b[u][0].w[i]) : 0.f;
                         if (g.b) t = fmaf(xv[i], __uint_as_float(b[u][1].w[i]), t);
-                        if (g.mn && xv[i] == __uint_as_float(b[u][2].w[i])) t += __uint_as_float(b[u][3].w[i]);
-                        if (g.mx && xv[i] == __uint_as_float(b[u][4].w[i])) t += __uint_as_float(b[u][5].w[i]);
+                        if (hit_mn && xv[i] == __uint_as_float(b[u][2].w[i])) t += __uint_as_float(gmn.w[i]);
+                        if (hit_mx && xv[i] == __uint_as_float(b[u][3].w[i])) t += __uint_as_float(gmx.w[i]);
                         acc[i] = SEGMENT ? t : __fadd_rn(acc[i], t);
                     }
                 }

@@ -93,15 +93,68 @@ def gcn_conv(x: Tensor, graph: CSRGraph, weight: Tensor, bias: Optional[Tensor])
     return Fn.aggregate(graph, xw, "sum")
 
 
+class _SageFused(torch.autograd.Function):
+    """One SAGEConv layer on a non-bipartite graph as ONE autograd node (sage_conv.py:120-152):
+        agg = aggr_j x_j;  y = act(agg W_l^T + x W_r^T + b)
+    forward  = gather-reduce sweep + one pair GEMM (two A streams into one TMEM accumulator, bias / ReLU in the epilogue);
+    backward = one pair GEMM for both input gradients (one read of g), the two split-K weight gradients, the bias column
+               sum, and the transposed sweep ACCUMULATING into the root gradient (out += A^T g_agg in the kernel epilogue)
+    -- no elementwise pass of size N x F exists in either direction except the ReLU mask."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w_l: Tensor, b_l: Optional[Tensor], w_r: Tensor, graph: CSRGraph, aggr: str, relu: bool):
+        x = x.contiguous()
+        agg = ops.spmm_csr(graph.rowptr, graph.col, graph.val, x, graph.num_dst, aggr, graph.plan)
+        w_hi, w_lo = dense.split_tf32(torch.cat([w_l.detach(), w_r.detach()], dim=1))
+        y, _ = dense.gemm_pair(agg, x, w_hi, w_lo, 0, w_l.size(0), bias=None if b_l is None else b_l.detach(), relu=relu)
+        ctx.graph, ctx.aggr, ctx.relu, ctx.has_bias = graph, aggr, relu, b_l is not None
+        ctx.save_for_backward(x, agg, w_hi, w_lo, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        x, agg, w_hi, w_lo, y = ctx.saved_tensors
+        graph = ctx.graph
+        g = g.contiguous()
+        if ctx.relu:
+            g = g * (y > 0)
+        k = x.size(1)
+        gx = gwl = gwr = gb = None
+        if ctx.needs_input_grad[0]:
+            ga, gx = dense.gemm_pair(g, None, w_hi, w_lo, 1, k, k)                   # g . [W_l | W_r]
+            graph.build_transpose()
+            val_t = graph.mean_val_t() if ctx.aggr == "mean" else graph.val_t
+            ops.spmm_csr(graph.rowptr_t, graph.col_t, val_t, ga, graph.num_src, "sum", graph.plan_t, out=gx, accumulate=True)
+        if ctx.needs_input_grad[1]:
+            gwl = dense._mm_tn(g, agg)
+        if ctx.needs_input_grad[3]:
+            gwr = dense._mm_tn(g, x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.column_sum(g)
+        return gx, gwl, gb, gwr, None, None, None
+
+
+def _sage_fusable(x_src: Tensor, x_dst: Optional[Tensor], graph: CSRGraph, aggr: str, w_l: Tensor, w_r: Optional[Tensor]) -> bool:
+    k, n = x_src.size(1), w_l.size(0)
+    return (x_dst is x_src and w_r is not None and aggr in ("mean", "sum", "add") and graph.val is None
+            and graph.num_src == graph.num_dst and x_src.is_cuda and x_src.dtype == torch.float32 and w_l.dtype == torch.float32
+            and dense.get_backend() == "tf32x3" and k % 128 == 0 and n % 128 == 0 and w_l.size(1) == k and w_r.size(1) == k
+            and x_src.size(0) > 0)
+
+
 def sage_conv(x_src: Tensor, x_dst: Optional[Tensor], graph: CSRGraph, aggr: str, w_l: Tensor, b_l: Optional[Tensor],
-              w_r: Optional[Tensor], normalize: bool = False) -> Tensor:
-    """SAGEConv.forward (sage_conv.py:120-152): lin_l(aggr_j x_j) + lin_r(x_i); the two products accumulate into
-    one output (dense.linear_pair) instead of two GEMMs, an add and their autograd nodes."""
-    agg = Fn.aggregate(graph, x_src, aggr)
-    if w_r is not None and x_dst is not None:
-        out = dense.linear_pair(agg, w_l, x_dst, w_r, b_l)
+              w_r: Optional[Tensor], normalize: bool = False, relu: bool = False) -> Tensor:
+    """SAGEConv.forward (sage_conv.py:120-152): act(lin_l(aggr_j x_j) + lin_r(x_i)).  Non-bipartite fp32 layers with
+    widths on the GEMM kernel's grid run as ONE autograd node (`_SageFused`); otherwise the two products still
+    accumulate into one output (dense.linear_pair)."""
+    if _sage_fusable(x_src, x_dst, graph, aggr, w_l, w_r):
+        out = _SageFused.apply(x_src, w_l, b_l, w_r, graph, "sum" if aggr == "add" else aggr, relu)
     else:
-        out = dense.linear(agg, w_l, b_l)
+        agg = Fn.aggregate(graph, x_src, aggr)
+        if w_r is not None and x_dst is not None:
+            out = dense.linear_pair(agg, w_l, x_dst, w_r, b_l, relu=relu)
+        else:
+            out = dense.linear(agg, w_l, b_l, relu=relu)
     if normalize:
         out = F.normalize(out, p=2.0, dim=-1)
     return out
