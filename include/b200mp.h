@@ -401,7 +401,7 @@ int b200mp_gemm_pair_tf32x3(const float* a1, int64_t k1, const float* a2, int64_
  * device (the tile -> segment map is rebuilt in shared memory), partial tiles at segment ends are stored row-masked.
  * b_layout 1: B_r = w[r] of a [n_seg, K, N] weight (c = a w[r]); b_layout 0: B_r = w[r] of a [n_seg, N, K] weight
  * (c = a w[r]^T: the input gradient of layout 1).  b_hi / b_lo from b200mp_split_tf32 over the whole stack.
- * k % 32 == 0, n % 128 == 0, n_seg <= 1024. */
+ * k % 32 == 0, n % 128 == 0, n_seg <= 256. */
 int b200mp_segment_matmul_tf32x3(const float* a, const int64_t* ptr, int64_t n_seg, const float* b_hi,
                                  const float* b_lo, int b_layout, float* c, int64_t m, int64_t k, int64_t n,
                                  void* stream);

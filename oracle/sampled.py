@@ -121,9 +121,9 @@ class _Dist:
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         if not self.on:
             return t.unsqueeze(0)
-        out = torch.empty((self.world, ) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.stack(parts)
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         if self.on:

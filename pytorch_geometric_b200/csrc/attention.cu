@@ -56,6 +56,14 @@ struct AttnArgs {
 
 __device__ __forceinline__ float leaky_f(float v, float slope) { return v > 0.0f ? v : v * slope; }
 
+// e^x as ONE multiply + ONE MUFU (ex2.approx: max relative error 2^-22.5, far inside the 1e-5 bar): the sweeps execute
+// two exponentials per edge and lane, and libm's expf costs ~8 issue slots each on kernels that are issue/latency bound.
+__device__ __forceinline__ float fexp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 __device__ __forceinline__ float head_sum(float v, int lph) {
     for (int o = lph >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -64,8 +72,8 @@ __device__ __forceinline__ float head_sum(float v, int lph) {
 // merge (m, s) softmax states: returns the two rescale factors
 __device__ __forceinline__ void merge_ms(float m1, float m2, float& M, float& c1, float& c2) {
     M = fmaxf(m1, m2);
-    c1 = (m1 == -__builtin_inff()) ? 0.0f : expf(m1 - M);
-    c2 = (m2 == -__builtin_inff()) ? 0.0f : expf(m2 - M);
+    c1 = (m1 == -__builtin_inff()) ? 0.0f : fexp(m1 - M);
+    c2 = (m2 == -__builtin_inff()) ? 0.0f : fexp(m2 - M);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -171,8 +179,8 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
                     for (int k = 0; k < VPL; ++k) {
                         if (!valid[k]) continue;
                         const float mn = fmaxf(m[k], l[k]);
-                        const float rs = expf(m[k] - mn);               // 0 on the first edge (m = -inf)
-                        const float p = expf(l[k] - mn);
+                        const float rs = fexp(m[k] - mn);               // 0 on the first edge (m = -inf)
+                        const float p = fexp(l[k] - mn);
                         s[k] = fmaf(s[k], rs, p);
 #pragma unroll
                         for (int i = 0; i < EPV; ++i) acc[k][i] = fmaf(acc[k][i], rs, p * f[k][i]);
@@ -261,8 +269,8 @@ attn_combine_kernel(T* __restrict__ out, float* __restrict__ row_max, float* __r
             for (int64_t c = c0 + slice; c < c1; c += n_slices) {
                 const float mc = part_ms[(c * heads + h) * 2], sc = part_ms[(c * heads + h) * 2 + 1];
                 const float Mn = fmaxf(M, mc);
-                const float r0 = (M == -__builtin_inff()) ? 0.0f : expf(M - Mn);
-                const float r1 = (mc == -__builtin_inff()) ? 0.0f : expf(mc - Mn);
+                const float r0 = (M == -__builtin_inff()) ? 0.0f : fexp(M - Mn);
+                const float r1 = (mc == -__builtin_inff()) ? 0.0f : fexp(mc - Mn);
                 S = S * r0 + sc * r1;
                 acc = acc * r0 + plan.partials[c * hc + f] * r1;
                 M = Mn;
@@ -427,7 +435,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
                 for (int k = 0; k < VPL; ++k) {
                     if (!valid[k]) continue;
                     const float score = MODE == ATTN_GAT ? leaky_f(l[k], a.slope) : l[k];
-                    const float alpha = expf(score - mrow[k]) * inv_den[k];
+                    const float alpha = fexp(score - mrow[k]) * inv_den[k];
                     const bool first = ((lig + k * G) * EPV) % a.chan == 0;
                     if (ALPHA_ONLY) {
                         if (first) alpha_out[e * a.heads + head[k]] = alpha;
@@ -521,7 +529,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
 
 // ------------------------------------------------------------------------------------------------ backward, source sweep
 template <typename T, typename I, int G, int VPL, int MODE>
-__global__ void __launch_bounds__(kAttnT, VPL == 1 ? 8 : 5)
+__global__ void __launch_bounds__(kAttnT)      // no register cap: capping at 64 serialised the row loads (8.0 -> 14.8 ms)
 attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t, const I* __restrict__ t2csr, AttnArgs a,
                     const T* __restrict__ grad_out, const float* __restrict__ pair, T* __restrict__ grad_v,
                     T* __restrict__ grad_k, float* __restrict__ grad_s_src, int64_t n_src, LongRowPlan plan) {

@@ -26,6 +26,7 @@ void set_error(const char* fmt, ...);
         cudaError_t e__ = (call);                                                               \
         if (e__ != cudaSuccess) {                                                               \
             ::b200mp::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            (void)cudaGetLastError(); /* do not leave the error pending for the caller's next CUDA call */ \
             return B200MP_ERR_CUDA;                                                             \
         }                                                                                       \
     } while (0)

@@ -56,6 +56,7 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uin
 
 // GROUPED: segment_matmul -- the row space is cut into segments (args.seg_ptr), every segment multiplies with its own B
 // block; tiles never straddle a segment (the last tile of a segment is partial and is stored with row-masked writes).
+constexpr int kMaxSegments = 256;
 struct GroupedTile {
     int m0, n0, seg, rows;     // first row, first column, segment, valid rows (<= 128)
 };
@@ -112,7 +113,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    __shared__ int tile_prefix[GROUPED ? 1026 : 1];
+    __shared__ int tile_prefix[GROUPED ? kMaxSegments + 2 : 1];   // (the dynamic stages leave ~1.7 KB of the 227 KB)
     if (GROUPED && threadIdx.x == 64) {                          // (an idle warp) tiles of 128 rows per segment, exclusive prefix
         int acc = 0;
         for (int r = 0; r < args.n_seg; ++r) {

@@ -107,3 +107,61 @@ def test_single_rank_plan_has_no_halo():
         assert plan.n_halo == 0 and plan.n_send == 0 and torch.equal(rel, src)
     finally:
         dist.destroy_process_group()
+
+
+def _sampled_worker(rank, world, port, q):
+    """bench.py's sampled-row checker (oracle/sampled.py) on 2 gloo ranks: every rank holds the in-edges of its node
+    range; rows / degrees of remote nodes travel through the checker's own small collectives.  Fed with the
+    single-process oracle's results on the unsharded graph it must report a tiny error -- and catch a corrupted shard."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from oracle import sampled
+        n_total, n_edges, Fi, Fo = 4000, 50000, 16, 24
+        rng = np.random.default_rng(7)
+        n_local = n_total // world
+        dst = ((rng.random(n_edges) ** 3) * (n_total - 1)).astype(np.int64)
+        dst[: n_total // 2] = rng.integers(0, n_total, size=n_total // 2)
+        src = rng.integers(0, n_total, size=n_edges)
+        x = rng.standard_normal((n_total, Fi)).astype(np.float32)
+        W = (rng.standard_normal((Fo, Fi)) / 4).astype(np.float32)
+        b = rng.standard_normal(Fo).astype(np.float32)
+        gout = rng.standard_normal((n_total, Fo)).astype(np.float32)
+        out = O.gcn_conv(x, src, dst, None, W, b)
+        gx, gw, gb = O.gcn_conv_backward(gout, x, src, dst, None, W)
+        lo = rank * n_local
+        mine = (dst >= lo) & (dst < lo + n_local)
+        t = torch.from_numpy
+        ei = t(np.stack([src[mine], dst[mine]]))
+        sl = slice(lo, lo + n_local)
+        args = (ei, lo, n_local, t(x[sl]), t(W), t(b), t(gout[sl]))
+        r = sampled.gcn_check(*args, t(out[sl]), t(gx[sl]), t(gw), t(gb), n_rows=256, max_edges=20000, seed=1)
+        assert r["ok"] and r["max_rel"] < 2e-6, r
+        bad = out[sl].copy()
+        if rank == 1:
+            bad += 1e-3
+        r2 = sampled.gcn_check(*args, t(bad), t(gx[sl]), t(gw), t(gb), n_rows=256, max_edges=20000, seed=1)
+        assert not r2["ok"], r2                     # the max over ranks is what every rank reports
+        q.put((rank, "ok"))
+    except Exception as exc:
+        import traceback
+        q.put((rank, "FAIL: " + "".join(traceback.format_exception(exc))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sampled_row_checker_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampled_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}: {msg}"
