@@ -64,7 +64,8 @@ def run_config(args, B):
         def model(xx):
             h = xx
             for i in range(L):
-                h = C.sage_conv(h, h, graph, "mean", Ws[2 * i], bs[i], Ws[2 * i + 1], relu=(i < L - 1))
+                h = C.sage_conv(h, h, graph, "mean", Ws[2 * i], bs[i], Ws[2 * i + 1], relu=(i < L - 1), input_is_relu=(i > 0),
+                                grad_masked_by_consumer=(i < L - 1))
             return h
 
         dom_op, dom_kernel = "spmm_csr", "csr_reduce_kernel (mean aggregation fwd on CSR / bwd on transposed CSR)"

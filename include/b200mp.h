@@ -145,13 +145,16 @@ int b200mp_csr_plan_fill(const void* rowptr, int64_t n_rows, int64_t chunk, int6
  * matrix is sharded by contiguous row ranges of peer_rows rows over the GPUs of the box and
  * peer_ptrs[r] is rank r's peer-mapped base address (torch symmetric memory / CUDA IPC); column c
  * is then gathered from peer_ptrs[c / peer_rows] + (c % peer_rows) * row_bytes, i.e. remote rows
- * come straight over NVLink inside this kernel -- the collective is fused into the gather. */
+ * come straight over NVLink inside this kernel -- the collective is fused into the gather.
+ * relu_mask (nullable, with flags bit 0): a [n_rows, feat] matrix of val_dtype; after the accumulate, out[i,f] is
+ * zeroed where relu_mask[i,f] <= 0 (rows without edges too) -- the ReLU backward of the producing layer fused into the
+ * last writer of its gradient (a layer's input x = relu(pre) is its own mask). */
 int b200mp_spmm_csr(const void* rowptr, const void* col, const float* val, const void* x,
                     void* out, int64_t n_rows, int64_t n_cols, int64_t feat, int reduce,
                     const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
                     int64_t n_chunks, int64_t chunk, float* partials, const float* bias,
                     const void* x_halo, int64_t n_local_cols, int flags, const void* peer_ptrs,
-                    int64_t peer_rows, int idx_dtype, int val_dtype, void* stream);
+                    int64_t peer_rows, const void* relu_mask, int idx_dtype, int val_dtype, void* stream);
 
 /* Segmented reduce without gather: out[i,:] = REDUCE_{e in [ptr[i], ptr[i+1])} src[e,:].
  * Replaces utils/_segment.py:11-50 (torch._segment_reduce / torch_scatter.segment_csr) and the
@@ -401,7 +404,7 @@ int b200mp_gemm_pair_tf32x3(const float* a1, int64_t k1, const float* a2, int64_
  * device (the tile -> segment map is rebuilt in shared memory), partial tiles at segment ends are stored row-masked.
  * b_layout 1: B_r = w[r] of a [n_seg, K, N] weight (c = a w[r]); b_layout 0: B_r = w[r] of a [n_seg, N, K] weight
  * (c = a w[r]^T: the input gradient of layout 1).  b_hi / b_lo from b200mp_split_tf32 over the whole stack.
- * k % 32 == 0, n % 128 == 0, n_seg <= 256. */
+ * k % 32 == 0, n % 128 == 0, n_seg <= 120. */
 int b200mp_segment_matmul_tf32x3(const float* a, const int64_t* ptr, int64_t n_seg, const float* b_hi,
                                  const float* b_lo, int b_layout, float* c, int64_t m, int64_t k, int64_t n,
                                  void* stream);

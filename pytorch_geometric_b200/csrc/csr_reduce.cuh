@@ -44,6 +44,11 @@ struct LongRowPlan {
     // straight over NVLink inside the kernel, no pack / exchange / unpack pass.
     const unsigned long long* peers;
     int64_t peer_rows;
+    // relu_mask != nullptr (with accumulate): after the add, out[i,f] is zeroed where relu_mask[i,f] <= 0 -- the ReLU
+    // backward of the layer that PRODUCED this layer's input, applied by the last writer of its gradient (the input
+    // x = relu(pre) is its own mask: x > 0 <=> pre > 0) instead of a separate 3-pass elementwise kernel.  Same dtype
+    // and shape as out; rows without edges are masked too.
+    const void* relu_mask;
 };
 
 // Base address of source row c for the three addressing modes (plain, [local | halo], peer table).
@@ -231,11 +236,18 @@ csr_reduce_kernel(const I* __restrict__ rowptr, const I* __restrict__ col,
                     for (int i = 0; i < EPV; ++i) f[i] = __fadd_rn(f[i], __ldg(bp + i));
                 }
                 if (plan.accumulate) {
-                    if (deg == 0) continue;
+                    if (deg == 0 && !plan.relu_mask) continue;
                     float o[EPV];
                     ElemTraits<T>::unpack(*reinterpret_cast<const Vec16*>(ob + static_cast<size_t>(vbase + lig + k * G) * 16), o);
 #pragma unroll
-                    for (int i = 0; i < EPV; ++i) f[i] = __fadd_rn(o[i], f[i]);
+                    for (int i = 0; i < EPV; ++i) f[i] = deg == 0 ? o[i] : __fadd_rn(o[i], f[i]);
+                    if (plan.relu_mask) {
+                        float mk[EPV];
+                        ElemTraits<T>::unpack(ldg_stream16(static_cast<const char*>(plan.relu_mask) + static_cast<size_t>(row) * row_bytes +
+                                                           static_cast<size_t>(vbase + lig + k * G) * 16), mk);
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) f[i] = mk[i] > 0.0f ? f[i] : 0.0f;
+                    }
                 }
                 stg_stream16(ob + static_cast<size_t>(vbase + lig + k * G) * 16, ElemTraits<T>::pack(f));
             }
@@ -259,6 +271,7 @@ csr_combine_kernel(const I* __restrict__ rowptr, T* __restrict__ out, int64_t fe
         acc = finalize<RED>(acc, deg, is_mean, inf_to_zero);
         if (bias) acc = __fadd_rn(acc, bias[f]);
         if (plan.accumulate) acc = __fadd_rn(ElemTraits<T>::to_float(out[row * feat + f]), acc);
+        if (plan.relu_mask && !(ElemTraits<T>::to_float(static_cast<const T*>(plan.relu_mask)[row * feat + f]) > 0.0f)) acc = 0.0f;
         out[row * feat + f] = ElemTraits<T>::from_float(acc);
     }
 }
@@ -303,8 +316,10 @@ csr_reduce_scalar_kernel(const I* __restrict__ rowptr, const I* __restrict__ col
             acc = finalize<RED>(acc, end - begin, is_mean, inf_to_zero);
             if (bias) acc = __fadd_rn(acc, bias[f]);
             if (plan.accumulate) {
-                if (end == begin) continue;
-                acc = __fadd_rn(ElemTraits<T>::to_float(out[row * feat + f]), acc);
+                if (end == begin && !plan.relu_mask) continue;
+                const float o = ElemTraits<T>::to_float(out[row * feat + f]);
+                acc = end == begin ? o : __fadd_rn(o, acc);
+                if (plan.relu_mask && !(ElemTraits<T>::to_float(static_cast<const T*>(plan.relu_mask)[row * feat + f]) > 0.0f)) acc = 0.0f;
             }
             out[row * feat + f] = ElemTraits<T>::from_float(acc);
         }

@@ -685,7 +685,7 @@ extern "C" int b200mp_segment_matmul_tf32x3(const float* a, const int64_t* ptr, 
     if (m == 0) return B200MP_OK;
     B200MP_CHECK_ARG(a && ptr && b_hi && b_lo && c && ok16(a) && ok16(b_hi) && ok16(b_lo) && ok16(c));
     if (k % 32 != 0 || n % kTsBN != 0 || n_seg > kMaxSegments || m > 0x7fffffffLL) {
-        set_error("segment_matmul_tf32x3: unsupported shape m=%lld k=%lld n=%lld segments=%lld (k %% 32, n %% 128, <= 256 segments)",
+        set_error("segment_matmul_tf32x3: unsupported shape m=%lld k=%lld n=%lld segments=%lld (k %% 32, n %% 128, <= 120 segments)",
                   (long long)m, (long long)k, (long long)n, (long long)n_seg);
         return B200MP_ERR_UNSUPPORTED;
     }

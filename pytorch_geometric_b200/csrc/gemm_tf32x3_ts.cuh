@@ -56,7 +56,7 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t a, uint32_t b, uin
 
 // GROUPED: segment_matmul -- the row space is cut into segments (args.seg_ptr), every segment multiplies with its own B
 // block; tiles never straddle a segment (the last tile of a segment is partial and is stored with row-masked writes).
-constexpr int kMaxSegments = 256;
+constexpr int kMaxSegments = 120;   // (120 + 2) ints stay inside ONE 1 KB granule next to 225.25 KB of dynamic stages (227 KB per CTA)
 struct GroupedTile {
     int m0, n0, seg, rows;     // first row, first column, segment, valid rows (<= 128)
 };

@@ -135,10 +135,11 @@ extern "C" int b200mp_spmm_csr(const void* rowptr, const void* col, const float*
                                const int64_t* long_rows, const int64_t* chunk_ptr,
                                int64_t n_long_rows, int64_t n_chunks, int64_t chunk, float* partials,
                                const float* bias, const void* x_halo, int64_t n_local_cols, int flags,
-                               const void* peer_ptrs, int64_t peer_rows, int idx_dtype, int val_dtype,
-                               void* stream) {
+                               const void* peer_ptrs, int64_t peer_rows, const void* relu_mask, int idx_dtype,
+                               int val_dtype, void* stream) {
     B200MP_CHECK_ARG(n_rows >= 0 && n_cols >= 0 && feat >= 0);
     B200MP_CHECK_ARG((flags & ~1) == 0 && (!(flags & 1) || (reduce == B200MP_SUM && !bias)));
+    B200MP_CHECK_ARG(!relu_mask || (flags & 1));
     if (n_rows == 0 || feat == 0) return B200MP_OK;
     B200MP_CHECK_ARG(rowptr && out);
     B200MP_CHECK_ARG(x || n_cols == 0 || peer_ptrs);
@@ -148,7 +149,7 @@ extern "C" int b200mp_spmm_csr(const void* rowptr, const void* col, const float*
     B200MP_CHECK_ARG(!x_halo || (n_local_cols >= 0 && n_local_cols <= n_cols));
     LongRowPlan plan{long_rows, chunk_ptr, n_long_rows, n_long_rows ? n_chunks : 0, chunk, partials,
                      x_halo, x_halo ? n_local_cols : 0, flags & 1,
-                     static_cast<const unsigned long long*>(peer_ptrs), peer_ptrs ? peer_rows : 0};
+                     static_cast<const unsigned long long*>(peer_ptrs), peer_ptrs ? peer_rows : 0, relu_mask};
     DISPATCH_T_I(spmm_typed, rowptr, col, val, x, out, n_rows, feat, reduce, plan, bias,
                  static_cast<cudaStream_t>(stream));
 }

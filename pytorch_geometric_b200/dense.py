@@ -301,7 +301,7 @@ def _grouped(a: Tensor, ptr: Tensor, w_hi: Tensor, w_lo: Tensor, b_layout: int, 
 def _grouped_ok(inputs: Tensor, other: Tensor) -> bool:
     R, k, n = other.shape
     return (_BACKEND == "tf32x3" and inputs.is_cuda and inputs.dtype == torch.float32 and other.dtype == torch.float32
-            and inputs.size(0) > 0 and k % 32 == 0 and n % 128 == 0 and R <= 256 and inputs.size(0) < 2**31)
+            and inputs.size(0) > 0 and k % 32 == 0 and n % 128 == 0 and R <= 120 and inputs.size(0) < 2**31)
 
 
 class _SegmentMatmul(torch.autograd.Function):

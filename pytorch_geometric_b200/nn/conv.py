@@ -102,13 +102,15 @@ class _SageFused(torch.autograd.Function):
     -- no elementwise pass of size N x F exists in either direction except the ReLU mask."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, w_l: Tensor, b_l: Optional[Tensor], w_r: Tensor, graph: CSRGraph, aggr: str, relu: bool):
+    def forward(ctx, x: Tensor, w_l: Tensor, b_l: Optional[Tensor], w_r: Tensor, graph: CSRGraph, aggr: str, relu: bool,
+                input_is_relu: bool, grad_masked_by_consumer: bool):
         x = x.contiguous()
         agg = ops.spmm_csr(graph.rowptr, graph.col, graph.val, x, graph.num_dst, aggr, graph.plan)
         w_hi, w_lo = dense.split_tf32(torch.cat([w_l.detach(), w_r.detach()], dim=1))
         y, _ = dense.gemm_pair(agg, x, w_hi, w_lo, 0, w_l.size(0), bias=None if b_l is None else b_l.detach(), relu=relu)
         ctx.graph, ctx.aggr, ctx.relu, ctx.has_bias = graph, aggr, relu, b_l is not None
-        ctx.save_for_backward(x, agg, w_hi, w_lo, y if relu else None)
+        ctx.input_is_relu, ctx.premasked = input_is_relu, grad_masked_by_consumer
+        ctx.save_for_backward(x, agg, w_hi, w_lo, y if (relu and not grad_masked_by_consumer) else None)
         return y
 
     @staticmethod
@@ -116,7 +118,7 @@ class _SageFused(torch.autograd.Function):
         x, agg, w_hi, w_lo, y = ctx.saved_tensors
         graph = ctx.graph
         g = g.contiguous()
-        if ctx.relu:
+        if ctx.relu and not ctx.premasked:
             g = g * (y > 0)
         k = x.size(1)
         gx = gwl = gwr = gb = None
@@ -124,14 +126,17 @@ class _SageFused(torch.autograd.Function):
             ga, gx = dense.gemm_pair(g, None, w_hi, w_lo, 1, k, k)                   # g . [W_l | W_r]
             graph.build_transpose()
             val_t = graph.mean_val_t() if ctx.aggr == "mean" else graph.val_t
-            ops.spmm_csr(graph.rowptr_t, graph.col_t, val_t, ga, graph.num_src, "sum", graph.plan_t, out=gx, accumulate=True)
+            # gx += A^T ga in the sweep's epilogue; when this layer's input is a ReLU output (x = relu(pre)), the same
+            # epilogue applies that ReLU's backward mask (x > 0), so the producing layer needs no elementwise pass
+            ops.spmm_csr(graph.rowptr_t, graph.col_t, val_t, ga, graph.num_src, "sum", graph.plan_t, out=gx, accumulate=True,
+                         relu_mask=x if ctx.input_is_relu else None)
         if ctx.needs_input_grad[1]:
             gwl = dense._mm_tn(g, agg)
         if ctx.needs_input_grad[3]:
             gwr = dense._mm_tn(g, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = ops.column_sum(g)
-        return gx, gwl, gb, gwr, None, None, None
+        return gx, gwl, gb, gwr, None, None, None, None, None
 
 
 def _sage_fusable(x_src: Tensor, x_dst: Optional[Tensor], graph: CSRGraph, aggr: str, w_l: Tensor, w_r: Optional[Tensor]) -> bool:
@@ -143,12 +148,19 @@ def _sage_fusable(x_src: Tensor, x_dst: Optional[Tensor], graph: CSRGraph, aggr:
 
 
 def sage_conv(x_src: Tensor, x_dst: Optional[Tensor], graph: CSRGraph, aggr: str, w_l: Tensor, b_l: Optional[Tensor],
-              w_r: Optional[Tensor], normalize: bool = False, relu: bool = False) -> Tensor:
+              w_r: Optional[Tensor], normalize: bool = False, relu: bool = False, input_is_relu: bool = False,
+              grad_masked_by_consumer: bool = False) -> Tensor:
     """SAGEConv.forward (sage_conv.py:120-152): act(lin_l(aggr_j x_j) + lin_r(x_i)).  Non-bipartite fp32 layers with
     widths on the GEMM kernel's grid run as ONE autograd node (`_SageFused`); otherwise the two products still
-    accumulate into one output (dense.linear_pair)."""
+    accumulate into one output (dense.linear_pair).
+
+    Stacking hints (both default False and are only honoured by the fused node; results are identical either way):
+    `input_is_relu` -- x is the output of a ReLU: the gradient this layer returns is masked by (x > 0) in the sweep's
+    epilogue; `grad_masked_by_consumer` -- this layer's `relu=True` output feeds ONLY a layer called with
+    `input_is_relu=True`, so its own backward skips the (idempotent) mask pass."""
     if _sage_fusable(x_src, x_dst, graph, aggr, w_l, w_r):
-        out = _SageFused.apply(x_src, w_l, b_l, w_r, graph, "sum" if aggr == "add" else aggr, relu)
+        out = _SageFused.apply(x_src, w_l, b_l, w_r, graph, "sum" if aggr == "add" else aggr, relu, input_is_relu,
+                               grad_masked_by_consumer and relu)
     else:
         agg = Fn.aggregate(graph, x_src, aggr)
         if w_r is not None and x_dst is not None:

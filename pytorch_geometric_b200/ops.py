@@ -262,7 +262,7 @@ class LongRowPlan:
 def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_rows: int, reduce: str = "sum",
              plan: Optional[LongRowPlan] = None, out: Optional[Tensor] = None,
              bias: Optional[Tensor] = None, x_halo: Optional[Tensor] = None, accumulate: bool = False,
-             peer_ptrs: Optional[int] = None, peer_rows: int = 0) -> Tensor:
+             peer_ptrs: Optional[int] = None, peer_rows: int = 0, relu_mask: Optional[Tensor] = None) -> Tensor:
     """out[i,:] = REDUCE_{e in row i} val[e] * x[col[e],:] (+ bias)  (x: [n_cols, F] contiguous)."""
     _cuda(rowptr, col, val, x)
     if x.dim() != 2:
@@ -285,6 +285,10 @@ def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_ro
             bias = bias.detach().float().contiguous()
         if bias.numel() != F:
             raise ValueError("bias must have one entry per feature")
+    if relu_mask is not None:
+        _cuda(relu_mask)
+        if not accumulate or relu_mask.dtype != x.dtype or tuple(relu_mask.shape) != (n_rows, F) or not relu_mask.is_contiguous():
+            raise ValueError("relu_mask needs accumulate=True and a contiguous [n_rows, F] tensor of x's dtype")
     n_cols, n_local = x.size(0), 0
     if x_halo is not None:
         _cuda(x_halo)
@@ -293,7 +297,7 @@ def spmm_csr(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, n_ro
         n_local, n_cols = x.size(0), x.size(0) + x_halo.size(0)
     _timed("spmm_csr", 2 if args[2] else 1, lib().b200mp_spmm_csr, _p(rowptr), _p(col), _p(val), _p(x), _p(out),
            n_rows, n_cols, F, REDUCE[reduce], *args, _p(bias), _p(x_halo), n_local, int(bool(accumulate)),
-           peer_ptrs, int(peer_rows), it, _vdt(x), _stream())
+           peer_ptrs, int(peer_rows), _p(relu_mask), it, _vdt(x), _stream())
     return out
 
 

@@ -127,3 +127,26 @@ def test_fused_sage_layer_forward_backward_vs_fp64(aggr, relu):
                                  (wr.grad, wrr.grad, "gWr", 2e-5), (bl.grad, blr.grad, "gb", 2e-5)):
         err = (got.double() - want).abs().max().item()
         assert err <= tol * max(want.abs().max().item(), 1e-6) * 4, f"{name}: {err:.3e} vs {want.abs().max().item():.3e}"
+
+
+def test_fused_sage_stack_with_relu_mask_in_the_sweep_epilogue():
+    """Two stacked fused SAGE layers with the ReLU backward of layer 1 applied by layer 2's accumulate epilogue
+    (input_is_relu / grad_masked_by_consumer): gradients equal the plain stacking of the same layers."""
+    n, e, F = 30_000, 400_000, 128
+    ei = synth_graph(n, e, 19, DEV)
+    g = torch.Generator(device=DEV).manual_seed(6)
+    graph = CSRGraph(ei[0], ei[1], n, n)
+    P = [(torch.randn(F, F, device=DEV, generator=g) / 11) for _ in range(4)]
+    bs = [torch.randn(F, device=DEV, generator=g) * 0.1 for _ in range(2)]
+    x0 = torch.randn(n, F, device=DEV, generator=g)
+    gout = torch.randn(n, F, device=DEV, generator=g)
+    res = []
+    for hints in (False, True):
+        x = x0.clone().requires_grad_()
+        ps = [p.clone().requires_grad_() for p in P]
+        h = C.sage_conv(x, x, graph, "mean", ps[0], bs[0], ps[1], relu=True, grad_masked_by_consumer=hints)
+        y = C.sage_conv(h, h, graph, "mean", ps[2], bs[1], ps[3], input_is_relu=hints)
+        y.backward(gout)
+        res.append([y.detach(), x.grad] + [p.grad for p in ps])
+    for a, b in zip(*res):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * b.abs().max().item())
