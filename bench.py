@@ -370,7 +370,7 @@ def run_b200(args):
         ops.set_option("gemm_prefetch", args.gemm_prefetch)
     if args.gemm_bsplit >= 0:
         dense.set_b_split(bool(args.gemm_bsplit))
-    torch.manual_seed(1234 + rank)
+    torch.manual_seed(1234)                  # the SAME layer parameters on every rank (what DDP's broadcast guarantees)
     conv = GCNConv(F, F, cached=True).to(dev)
     with torch.no_grad():
         conv.bias.normal_(0, 0.1)

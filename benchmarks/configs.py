@@ -43,6 +43,8 @@ def run_config(args, B):
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
+    if os.environ.get("B200MP_ATTN_STAGED") is not None:           # A/B switch of the cp.async-staged attention forward
+        ops.set_option("attn_staged", int(os.environ["B200MP_ATTN_STAGED"]))
     cfg = args.config
     peak, peak_src = B.measured_peaks()
     gen = torch.Generator(device=dev).manual_seed(100 + cfg)

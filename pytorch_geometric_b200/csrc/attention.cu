@@ -39,6 +39,8 @@ namespace b200mp {
 
 enum { ATTN_GAT = 0, ATTN_GATV2 = 1, ATTN_DOT = 2 };
 
+int get_option_attn_staged();   // b200mp_set_option("attn_staged", 0 | 1): cp.async-staged forward (default 1)
+
 constexpr int kAttnT = 128;   // 4 warps = 4 work items per CTA
 
 struct AttnArgs {
@@ -69,6 +71,18 @@ __device__ __forceinline__ float head_sum(float v, int lph) {
     return v;
 }
 
+// cp.async (LDGSTS) into a LANE-PRIVATE shared-memory slot: the gathered row vector a lane will consume itself, fetched one
+// loop iteration ahead without holding registers (the issuing thread's own wait_group makes it visible to itself).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // merge (m, s) softmax states: returns the two rescale factors
 __device__ __forceinline__ void merge_ms(float m1, float m2, float& M, float& c1, float& c2) {
     M = fmaxf(m1, m2);
@@ -77,7 +91,10 @@ __device__ __forceinline__ void merge_ms(float m1, float m2, float& M, float& c1
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <typename T, typename I, int G, int VPL, int MODE>
+// STAGED (VPL == 1, G >= 8): the row vectors (and GAT's a_src scalars) of iteration t + 1 are in flight as cp.async
+// copies into lane-private shared-memory slots while iteration t is computed -- twice the rows in flight per warp at the
+// same register budget (the sweeps are latency-bound: 58 % long-scoreboard stalls in profiles/r2_attn_v2.summary.csv).
+template <typename T, typename I, int G, int VPL, int MODE, bool STAGED = false>
 __global__ void __launch_bounds__(kAttnT, VPL == 1 ? 8 : 5)       // <= 64 registers: 32 warps / SM (latency-bound gather)
 attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArgs a, T* __restrict__ out,
                 float* __restrict__ row_max, float* __restrict__ row_den, int64_t n_rows, LongRowPlan plan,
@@ -115,6 +132,94 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
         }
     }
 
+    if constexpr (STAGED) {
+        static_assert(VPL == 1 && S * UNR <= 32, "staged path: one vector per lane, an iteration inside one index batch");
+        extern __shared__ __align__(16) unsigned char attn_stage[];
+        constexpr int D = 2;                                        // slots: iteration t and t + 1
+        constexpr int NV = MODE == ATTN_DOT ? 2 : 1;                // value (+ key) vector per edge
+        constexpr int PER = S * UNR;                                // edges per iteration of the warp
+        unsigned char* vslots = attn_stage + static_cast<size_t>(threadIdx.x) * 16;
+        float* sslots = reinterpret_cast<float*>(attn_stage + static_cast<size_t>(D) * UNR * NV * kAttnT * 16) + threadIdx.x;
+        auto vslot = [&](int d, int u, int v) { return vslots + static_cast<size_t>((d * UNR + u) * NV + v) * (kAttnT * 16); };
+        auto sslot = [&](int d, int u) { return sslots + (d * UNR + u) * kAttnT; };
+        const int deg = static_cast<int>(end - begin);
+        const int n_it = (deg + PER - 1) / PER;
+        const size_t off = static_cast<size_t>(lig) * 16;
+        int cb = 0;                                                 // index batch held in c0 (c1 = the next one)
+        I c0 = (lane < deg) ? ldg_idx(col + begin + lane) : I(0);
+        I c1 = (32 + lane < deg) ? ldg_idx(col + begin + 32 + lane) : I(0);
+        auto issue = [&](int t) {
+            const int d = t & (D - 1);
+            const I creg = ((t * PER) >> 5) == cb ? c0 : c1;        // warp-uniform choice
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int j = t * PER + u * S + sub;
+                const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, creg, j & 31));
+                if (j < deg && valid[0]) {
+                    cp_async16(vslot(d, u, 0), a.v + static_cast<size_t>(c) * a.v_stride + off);
+                    if (MODE == ATTN_DOT) cp_async16(vslot(d, u, 1), a.k + static_cast<size_t>(c) * a.k_stride + off);
+                    if (MODE == ATTN_GAT) cp_async4(sslot(d, u), a.s_src + c * a.heads + head[0]);
+                }
+            }
+            cp_async_commit();
+        };
+        // invariant: issue(t) needs index batch (t * PER) >> 5 in {cb, cb + 1} (PER divides 32, so an iteration never
+        // straddles a batch); once the issue stream has moved on to batch cb + 1, batch cb is dead: rotate and fetch
+        // batch cb + 2, a whole batch before it is needed
+        if (n_it > 0) issue(0);
+        for (int t = 0; t < n_it; ++t) {
+            if (t + 1 < n_it) {
+                issue(t + 1);
+                if ((((t + 1) * PER) >> 5) > cb) {
+                    c0 = c1;
+                    ++cb;
+                    c1 = ((cb + 1) * 32 + lane < deg) ? ldg_idx(col + begin + (cb + 1) * 32 + lane) : I(0);
+                }
+            } else {
+                cp_async_commit();
+            }
+            cp_async_wait<1>();
+            const int d = t & (D - 1);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int j = t * PER + u * S + sub;
+                const bool ev = j < deg;
+                float f[EPV], l = 0.0f;
+                if (ev && valid[0]) {
+                    ElemTraits<T>::unpack(*reinterpret_cast<const Vec16*>(vslot(d, u, 0)), f);
+                    if (MODE == ATTN_GAT) {
+                        float sc = *sslot(d, u);
+                        if (a.s_edge) sc += __ldg(a.s_edge + (begin + j) * a.heads + head[0]);
+                        l = leaky_f(sc + sd[0], a.slope);
+                    }
+                    if (MODE == ATTN_GATV2) {
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) l = fmaf(av[0][i], leaky_f(f[i] + qv[0][i], a.slope), l);
+                    }
+                    if (MODE == ATTN_DOT) {
+                        float kf[EPV];
+                        ElemTraits<T>::unpack(*reinterpret_cast<const Vec16*>(vslot(d, u, 1)), kf);
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) l = fmaf(qv[0][i], kf[i], l);
+                    }
+                }
+                if (MODE != ATTN_GAT) {
+                    l = head_sum(l, a.lph);
+                    if (MODE == ATTN_DOT) l *= a.scale;
+                }
+                if (ev && valid[0]) {
+                    const float mn = fmaxf(m[0], l);
+                    const float rs = fexp(m[0] - mn);
+                    const float p = fexp(l - mn);
+                    s[0] = fmaf(s[0], rs, p);
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) acc[0][i] = fmaf(acc[0][i], rs, p * f[i]);
+                    m[0] = mn;
+                }
+            }
+        }
+        cp_async_wait<0>();
+    } else {
     // Column indices are loaded by the whole warp, 32 edges at a time (coalesced, one batch ahead of the row loads so
     // the index latency is off the critical path) and handed to the lane groups by shuffle.
     I c_next = (begin + lane < end) ? ldg_idx(col + begin + lane) : I(0);
@@ -190,6 +295,7 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
             }
         }
     }
+    }   // !STAGED
     // merge the S lane groups (they walked disjoint edges of the same row)
 #pragma unroll
     for (int o = G; o < 32; o <<= 1) {
@@ -747,7 +853,17 @@ int attn_forward_typed(const void* rowptr_, const void* col_, AttnArgs a, void* 
     const int64_t items = plan.n_chunks + n_rows;
     const unsigned blocks = static_cast<unsigned>(ceil_div(items, kAttnT / 32));
 #define ATTN_FWD(G_, V_) attn_fwd_kernel<T, I, G_, V_, MODE><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, out, row_max, row_den, n_rows, plan, part_ms)
-    ATTN_BY_SHAPE(ATTN_FWD);
+#define ATTN_FWD_STAGED(G_) attn_fwd_kernel<T, I, G_, 1, MODE, true><<<blocks, kAttnT, stage_bytes, s>>>(rowptr, col, a, out, row_max, row_den, n_rows, plan, part_ms)
+    // lane-private cp.async slots: 2 iterations x 4 edges x (value (+ key) vector + a_src scalar) per thread
+    const size_t stage_bytes = static_cast<size_t>(2) * 4 * kAttnT * ((MODE == ATTN_DOT ? 2 : 1) * 16 + 4);
+    if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
+        if (n_vec <= 8) ATTN_FWD_STAGED(8);
+        else if (n_vec <= 16) ATTN_FWD_STAGED(16);
+        else ATTN_FWD_STAGED(32);
+    } else {
+        ATTN_BY_SHAPE(ATTN_FWD);
+    }
+#undef ATTN_FWD_STAGED
 #undef ATTN_FWD
     B200MP_LAUNCH_CHECK();
     if (plan.n_long > 0) {

@@ -54,6 +54,8 @@ static int g_gemm_mode = 1;   // TS mode (A operand in TMEM) measured 25 % faste
 int get_option_gemm_mode() { return g_gemm_mode; }
 static int g_spmm_tune = 0;
 int get_option_spmm_tune() { return g_spmm_tune; }
+static int g_attn_staged = 1;   // cp.async-staged attention forward (csrc/attention.cu); 0 = register-staged loop
+int get_option_attn_staged() { return g_attn_staged; }
 
 // Work counters of the persistent kernels: a small device-resident pool, one slot per launch in
 // round-robin order, zeroed on the launching stream right before the kernel (so concurrent
@@ -92,6 +94,11 @@ extern "C" int b200mp_set_option(const char* name, int value) {
     }
     if (strcmp(name, "spmm_tune") == 0) {
         b200mp::g_spmm_tune = value;
+        return B200MP_OK;
+    }
+    if (strcmp(name, "attn_staged") == 0) {
+        if (value != 0 && value != 1) return B200MP_ERR_INVALID_ARG;
+        b200mp::g_attn_staged = value;
         return B200MP_OK;
     }
     if (strcmp(name, "gemm_prefetch") == 0) {
