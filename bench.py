@@ -286,6 +286,13 @@ def run_parity(args, conv, fwd, step, ei, x, gout, rank, world, dev):
     return res
 
 
+# Both sides of this comparison are fp32 engine results that differ only in summation order (per-rank partial weight
+# gradients + all_reduce vs one split-K GEMM; shard-local vs global edge order), and the difference is measured against
+# the row's largest |value|, not against sum|terms| -- so the bound is looser than parity_check's 1e-5 (which is the
+# oracle comparison).  Measured: 1.8e-5 at N = 2.
+SHARD_TOL = 1e-4
+
+
 def shard_vs_unsharded(args, conv, rank, world, dev, n_small=100_000, e_small=1_000_000):
     """Every rank builds the WHOLE small graph (all ranks' seeded edge lists), runs the single-GPU engine on it, and
     compares its own rows with what the sharded path (same builder, same kernels, same barriers as the timed loop)
@@ -336,7 +343,7 @@ def shard_vs_unsharded(args, conv, rank, world, dev, n_small=100_000, e_small=1_
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     conv.zero_grad(set_to_none=True)
     return {"nodes": world * n_small, "edges": world * e_small, "p_local": args.p_local, "path": args.dist,
-            "max_rel": float(t.item()), "tol": 2e-5, "ok": bool(t.item() <= 2e-5), "per_quantity_rank0": per}
+            "max_rel": float(t.item()), "tol": SHARD_TOL, "ok": bool(t.item() <= SHARD_TOL), "per_quantity_rank0": per}
 
 
 # --------------------------------------------------------------------------- the B200 arm

@@ -76,6 +76,9 @@ __device__ __forceinline__ float head_sum(float v, int lph) {
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
 }
@@ -409,7 +412,7 @@ attn_combine_kernel(T* __restrict__ out, float* __restrict__ row_max, float* __r
 
 // ------------------------------------------------------------------------------------------------ backward, destination sweep
 // Also the alpha writer of the forward (ALPHA_ONLY: alpha[e,h] from the saved statistics, nothing else).
-template <typename T, typename I, int G, int VPL, int MODE, bool ALPHA_ONLY>
+template <typename T, typename I, int G, int VPL, int MODE, bool ALPHA_ONLY, bool STAGED = false>
 __global__ void __launch_bounds__(kAttnT)
 attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArgs a, const float* __restrict__ row_max,
                     const float* __restrict__ row_den, const T* __restrict__ out, const T* __restrict__ grad_out,
@@ -471,105 +474,173 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
             for (int k = 0; k < VPL; ++k) D[k] = head_sum(D[k], a.lph);
         }
 
-        I c_next = (begin + lane < end) ? ldg_idx(col + begin + lane) : I(0);
-        for (int64_t b0 = begin; b0 < end; b0 += 32) {
-        const I c_cur = c_next;
-        const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
-        c_next = (b0 + 32 + lane < end) ? ldg_idx(col + b0 + 32 + lane) : I(0);
-        for (int j0 = 0; j0 < nb; j0 += S * UNR) {
-            const int64_t e0 = b0 + j0;
-            Vec16 vb[UNR][VPL], kb[UNR][VPL];
-            float sc[UNR][VPL];
-            bool ev[UNR];
+        // one edge of this lane group: vbv / kbv = the gathered value (/ key) vectors, scv = GAT's a_src(+a_edge) scalars
+        auto process = [&](int64_t e, bool evu, const Vec16* vbv, const Vec16* kbv, const float* scv) {
+            float f[VPL][EPV], kf[VPL][EPV], l[VPL], dot[VPL];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int jj = j0 + u * S + sub;
-                const int64_t e = b0 + jj;
-                ev[u] = jj < nb;
-                const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, c_cur, jj & 31));
-                if (ev[u]) {
+            for (int k = 0; k < VPL; ++k) {
+                l[k] = dot[k] = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < VPL; ++k) {
-                        if (!valid[k]) continue;
-                        const size_t off = static_cast<size_t>(lig + k * G) * 16;
-                        if (!ALPHA_ONLY || MODE == ATTN_GATV2) vb[u][k] = ldg_row16(a.v + static_cast<size_t>(c) * a.v_stride + off);
-                        if (MODE == ATTN_DOT) kb[u][k] = ldg_row16(a.k + static_cast<size_t>(c) * a.k_stride + off);
-                        if (MODE == ATTN_GAT) {
-                            sc[u][k] = __ldg(a.s_src + c * a.heads + head[k]);
-                            if (a.s_edge) sc[u][k] += __ldg(a.s_edge + e * a.heads + head[k]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int64_t e = e0 + u * S + sub;
-                float f[VPL][EPV], kf[VPL][EPV], l[VPL], dot[VPL];
-#pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    l[k] = dot[k] = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < EPV; ++i) f[k][i] = kf[k][i] = 0.0f;
-                    if (ev[u] && valid[k]) {
-                        if (!ALPHA_ONLY || MODE == ATTN_GATV2) ElemTraits<T>::unpack(vb[u][k], f[k]);
-                        if (MODE == ATTN_GAT) l[k] = sc[u][k] + sd[k];                       // pre-activation
-                        if (MODE == ATTN_GATV2) {
-#pragma unroll
-                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i], a.slope), l[k]);
-                        }
-                        if (MODE == ATTN_DOT) {
-                            ElemTraits<T>::unpack(kb[u][k], kf[k]);
-#pragma unroll
-                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(qv[k][i], kf[k][i], l[k]);
-                        }
-                        if (!ALPHA_ONLY) {
-#pragma unroll
-                            for (int i = 0; i < EPV; ++i) dot[k] = fmaf(gv[k][i], f[k][i], dot[k]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    if (MODE != ATTN_GAT) {
-                        l[k] = head_sum(l[k], a.lph);
-                        if (MODE == ATTN_DOT) l[k] *= a.scale;
-                    }
-                    if (!ALPHA_ONLY) dot[k] = head_sum(dot[k], a.lph);
-                }
-                if (!ev[u]) continue;
-#pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    if (!valid[k]) continue;
-                    const float score = MODE == ATTN_GAT ? leaky_f(l[k], a.slope) : l[k];
-                    const float alpha = fexp(score - mrow[k]) * inv_den[k];
-                    const bool first = ((lig + k * G) * EPV) % a.chan == 0;
-                    if (ALPHA_ONLY) {
-                        if (first) alpha_out[e * a.heads + head[k]] = alpha;
-                        continue;
-                    }
-                    float gs = alpha * (dot[k] - D[k]);
-                    if (MODE == ATTN_GAT) {
-                        gs *= (l[k] > 0.0f ? 1.0f : a.slope);
-                        if (first) gsd[k] += gs;
-                    }
+                for (int i = 0; i < EPV; ++i) f[k][i] = kf[k][i] = 0.0f;
+                if (evu && valid[k]) {
+                    if (!ALPHA_ONLY || MODE == ATTN_GATV2) ElemTraits<T>::unpack(vbv[k], f[k]);
+                    if (MODE == ATTN_GAT) l[k] = scv[k] + sd[k];                         // pre-activation
                     if (MODE == ATTN_GATV2) {
 #pragma unroll
-                        for (int i = 0; i < EPV; ++i) {
-                            const float z = f[k][i] + qv[k][i];
-                            gq[k][i] = fmaf(gs * av[k][i], (z > 0.0f ? 1.0f : a.slope), gq[k][i]);
-                            gatt[k][i] = fmaf(gs, leaky_f(z, a.slope), gatt[k][i]);
-                        }
+                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i], a.slope), l[k]);
                     }
                     if (MODE == ATTN_DOT) {
-                        gs *= a.scale;
+                        ElemTraits<T>::unpack(kbv[k], kf[k]);
 #pragma unroll
-                        for (int i = 0; i < EPV; ++i) gq[k][i] = fmaf(gs, kf[k][i], gq[k][i]);
+                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(qv[k][i], kf[k][i], l[k]);
                     }
-                    if (first) *reinterpret_cast<float2*>(pair + (e * a.heads + head[k]) * 2) = make_float2(alpha, gs);
+                    if (!ALPHA_ONLY) {
+#pragma unroll
+                        for (int i = 0; i < EPV; ++i) dot[k] = fmaf(gv[k][i], f[k][i], dot[k]);
+                    }
                 }
             }
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                if (MODE != ATTN_GAT) {
+                    l[k] = head_sum(l[k], a.lph);
+                    if (MODE == ATTN_DOT) l[k] *= a.scale;
+                }
+                if (!ALPHA_ONLY) dot[k] = head_sum(dot[k], a.lph);
+            }
+            if (!evu) return;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                if (!valid[k]) continue;
+                const float score = MODE == ATTN_GAT ? leaky_f(l[k], a.slope) : l[k];
+                const float alpha = fexp(score - mrow[k]) * inv_den[k];
+                const bool first = ((lig + k * G) * EPV) % a.chan == 0;
+                if (ALPHA_ONLY) {
+                    if (first) alpha_out[e * a.heads + head[k]] = alpha;
+                    continue;
+                }
+                float gs = alpha * (dot[k] - D[k]);
+                if (MODE == ATTN_GAT) {
+                    gs *= (l[k] > 0.0f ? 1.0f : a.slope);
+                    if (first) gsd[k] += gs;
+                }
+                if (MODE == ATTN_GATV2) {
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) {
+                        const float z = f[k][i] + qv[k][i];
+                        gq[k][i] = fmaf(gs * av[k][i], (z > 0.0f ? 1.0f : a.slope), gq[k][i]);
+                        gatt[k][i] = fmaf(gs, leaky_f(z, a.slope), gatt[k][i]);
+                    }
+                }
+                if (MODE == ATTN_DOT) {
+                    gs *= a.scale;
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) gq[k][i] = fmaf(gs, kf[k][i], gq[k][i]);
+                }
+                if (first) *reinterpret_cast<float2*>(pair + (e * a.heads + head[k]) * 2) = make_float2(alpha, gs);
+            }
+        };
+
+        if constexpr (STAGED) {
+            // cp.async-staged gather (see attn_fwd_kernel): iteration t + 1 in flight in lane-private shared-memory slots
+            static_assert(VPL == 1 && S * UNR <= 32, "staged path: one vector per lane");
+            extern __shared__ __align__(16) unsigned char attn_stage[];
+            constexpr int D = 2, NV = MODE == ATTN_DOT ? 2 : 1, PER = S * UNR;
+            unsigned char* vslots = attn_stage + static_cast<size_t>(threadIdx.x) * 16;
+            float* sslots = reinterpret_cast<float*>(attn_stage + static_cast<size_t>(D) * UNR * NV * kAttnT * 16) + threadIdx.x;
+            auto vslot = [&](int d, int u, int v) { return vslots + static_cast<size_t>((d * UNR + u) * NV + v) * (kAttnT * 16); };
+            auto sslot = [&](int d, int u) { return sslots + (d * UNR + u) * kAttnT; };
+            const int deg = static_cast<int>(end - begin);
+            const int n_it = (deg + PER - 1) / PER;
+            const size_t off = static_cast<size_t>(lig) * 16;
+            int cb = 0;
+            I c0 = (lane < deg) ? ldg_idx(col + begin + lane) : I(0);
+            I c1 = (32 + lane < deg) ? ldg_idx(col + begin + 32 + lane) : I(0);
+            auto issue = [&](int t) {
+                const int d = t & (D - 1);
+                const I creg = ((t * PER) >> 5) == cb ? c0 : c1;
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int j = t * PER + u * S + sub;
+                    const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, creg, j & 31));
+                    if (j < deg && valid[0]) {
+                        if (!ALPHA_ONLY || MODE == ATTN_GATV2) cp_async16(vslot(d, u, 0), a.v + static_cast<size_t>(c) * a.v_stride + off);
+                        if (MODE == ATTN_DOT) cp_async16(vslot(d, u, 1), a.k + static_cast<size_t>(c) * a.k_stride + off);
+                        if (MODE == ATTN_GAT) cp_async4(sslot(d, u), a.s_src + c * a.heads + head[0]);
+                    }
+                }
+                cp_async_commit();
+            };
+            if (n_it > 0) issue(0);
+            for (int t = 0; t < n_it; ++t) {
+                if (t + 1 < n_it) {
+                    issue(t + 1);
+                    if ((((t + 1) * PER) >> 5) > cb) {
+                        c0 = c1;
+                        ++cb;
+                        c1 = ((cb + 1) * 32 + lane < deg) ? ldg_idx(col + begin + (cb + 1) * 32 + lane) : I(0);
+                    }
+                } else {
+                    cp_async_commit();
+                }
+                cp_async_wait<1>();
+                const int d = t & (D - 1);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int j = t * PER + u * S + sub;
+                    const bool evu = j < deg;
+                    const int64_t e = begin + j;
+                    Vec16 v0 = {}, k0 = {};
+                    float sc0 = 0.0f;
+                    if (evu && valid[0]) {
+                        if (!ALPHA_ONLY || MODE == ATTN_GATV2) v0 = *reinterpret_cast<const Vec16*>(vslot(d, u, 0));
+                        if (MODE == ATTN_DOT) k0 = *reinterpret_cast<const Vec16*>(vslot(d, u, 1));
+                        if (MODE == ATTN_GAT) {
+                            sc0 = *sslot(d, u);
+                            if (a.s_edge) sc0 += __ldg(a.s_edge + e * a.heads + head[0]);
+                        }
+                    }
+                    process(e, evu, &v0, &k0, &sc0);
+                }
+            }
+            cp_async_wait<0>();
+        } else {
+        I c_next = (begin + lane < end) ? ldg_idx(col + begin + lane) : I(0);
+        for (int64_t b0 = begin; b0 < end; b0 += 32) {
+            const I c_cur = c_next;
+            const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
+            c_next = (b0 + 32 + lane < end) ? ldg_idx(col + b0 + 32 + lane) : I(0);
+            for (int j0 = 0; j0 < nb; j0 += S * UNR) {
+                Vec16 vb[UNR][VPL], kb[UNR][VPL];
+                float sc[UNR][VPL];
+                bool ev[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int jj = j0 + u * S + sub;
+                    const int64_t e = b0 + jj;
+                    ev[u] = jj < nb;
+                    const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, c_cur, jj & 31));
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) sc[u][k] = 0.0f;
+                    if (ev[u]) {
+#pragma unroll
+                        for (int k = 0; k < VPL; ++k) {
+                            if (!valid[k]) continue;
+                            const size_t off = static_cast<size_t>(lig + k * G) * 16;
+                            if (!ALPHA_ONLY || MODE == ATTN_GATV2) vb[u][k] = ldg_row16(a.v + static_cast<size_t>(c) * a.v_stride + off);
+                            if (MODE == ATTN_DOT) kb[u][k] = ldg_row16(a.k + static_cast<size_t>(c) * a.k_stride + off);
+                            if (MODE == ATTN_GAT) {
+                                sc[u][k] = __ldg(a.s_src + c * a.heads + head[k]);
+                                if (a.s_edge) sc[u][k] += __ldg(a.s_edge + e * a.heads + head[k]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) process(b0 + j0 + u * S + sub, ev[u], vb[u], kb[u], sc[u]);
+            }
         }
-        }
+        }   // !STAGED
         if (ALPHA_ONLY) continue;
         // sum the lane groups' per-row partial gradients
 #pragma unroll
@@ -634,7 +705,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
 }
 
 // ------------------------------------------------------------------------------------------------ backward, source sweep
-template <typename T, typename I, int G, int VPL, int MODE>
+template <typename T, typename I, int G, int VPL, int MODE, bool STAGED = false>
 __global__ void __launch_bounds__(kAttnT)      // no register cap: capping at 64 serialised the row loads (8.0 -> 14.8 ms)
 attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t, const I* __restrict__ t2csr, AttnArgs a,
                     const T* __restrict__ grad_out, const float* __restrict__ pair, T* __restrict__ grad_v,
@@ -669,67 +740,135 @@ attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t,
             for (int i = 0; i < EPV; ++i) av[k][i] = __ldg(a.att + v * EPV + i);
         }
     }
+    // one out-edge: gv = the destination's gradient row vector, qv_ = its x_r / query row vector, pr = (alpha, grad_score)
+    auto consume = [&](const Vec16* gv, const Vec16* qv_, const float2* pr) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            if (!valid[k]) continue;
+            float g[EPV];
+            ElemTraits<T>::unpack(gv[k], g);
+            const float alpha = pr[k].x, gs = pr[k].y;
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) accv[k][i] = fmaf(alpha, g[i], accv[k][i]);
+            if (MODE == ATTN_GAT) gss[k] += gs;
+            if (MODE != ATTN_GAT) {
+                float qf[EPV];
+                ElemTraits<T>::unpack(qv_[k], qf);
+                if (MODE == ATTN_GATV2) {
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) accv[k][i] = fmaf(gs * av[k][i], ((xl[k][i] + qf[i]) > 0.0f ? 1.0f : a.slope), accv[k][i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) acck[k][i] = fmaf(gs, qf[i], acck[k][i]);
+                }
+            }
+        }
+    };
+    if constexpr (STAGED) {
+        static_assert(VPL == 1 && S * UNR <= 32, "staged path: one vector per lane");
+        extern __shared__ __align__(16) unsigned char attn_stage[];
+        constexpr int D = 2, NV = MODE == ATTN_GAT ? 1 : 2, PER = S * UNR;
+        unsigned char* vslots = attn_stage + static_cast<size_t>(threadIdx.x) * 16;
+        float2* pslots = reinterpret_cast<float2*>(attn_stage + static_cast<size_t>(D) * UNR * NV * kAttnT * 16) + threadIdx.x;
+        auto vslot = [&](int d, int u, int v) { return vslots + static_cast<size_t>((d * UNR + u) * NV + v) * (kAttnT * 16); };
+        auto pslot = [&](int d, int u) { return pslots + (d * UNR + u) * kAttnT; };
+        const int deg = static_cast<int>(end - begin);
+        const int n_it = (deg + PER - 1) / PER;
+        const size_t off = static_cast<size_t>(lig) * 16;
+        int cb = 0;
+        I d0 = 0, p0 = 0, d1 = 0, p1 = 0;
+        if (lane < deg) { d0 = ldg_idx(col_t + begin + lane); p0 = ldg_idx(t2csr + begin + lane); }
+        if (32 + lane < deg) { d1 = ldg_idx(col_t + begin + 32 + lane); p1 = ldg_idx(t2csr + begin + 32 + lane); }
+        auto issue = [&](int t) {
+            const int d = t & (D - 1);
+            const bool cur = ((t * PER) >> 5) == cb;
+            const I dreg = cur ? d0 : d1, preg = cur ? p0 : p1;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int j = t * PER + u * S + sub;
+                const int64_t dd = static_cast<int64_t>(__shfl_sync(0xffffffffu, dreg, j & 31));
+                const int64_t pp = static_cast<int64_t>(__shfl_sync(0xffffffffu, preg, j & 31));
+                if (j < deg && valid[0]) {
+                    cp_async16(vslot(d, u, 0), gb + static_cast<size_t>(dd) * row_bytes + off);
+                    if (MODE != ATTN_GAT) cp_async16(vslot(d, u, 1), a.q + static_cast<size_t>(dd) * a.q_stride + off);
+                    cp_async8(pslot(d, u), reinterpret_cast<const float2*>(pair) + pp * a.heads + head[0]);
+                }
+            }
+            cp_async_commit();
+        };
+        if (n_it > 0) issue(0);
+        for (int t = 0; t < n_it; ++t) {
+            if (t + 1 < n_it) {
+                issue(t + 1);
+                if ((((t + 1) * PER) >> 5) > cb) {
+                    d0 = d1;
+                    p0 = p1;
+                    ++cb;
+                    d1 = p1 = 0;
+                    if ((cb + 1) * 32 + lane < deg) {
+                        d1 = ldg_idx(col_t + begin + (cb + 1) * 32 + lane);
+                        p1 = ldg_idx(t2csr + begin + (cb + 1) * 32 + lane);
+                    }
+                }
+            } else {
+                cp_async_commit();
+            }
+            cp_async_wait<1>();
+            const int d = t & (D - 1);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int j = t * PER + u * S + sub;
+                if (j < deg && valid[0]) {
+                    const Vec16 g0 = *reinterpret_cast<const Vec16*>(vslot(d, u, 0));
+                    Vec16 q0 = {};
+                    if (MODE != ATTN_GAT) q0 = *reinterpret_cast<const Vec16*>(vslot(d, u, 1));
+                    const float2 pr0 = *pslot(d, u);
+                    consume(&g0, &q0, &pr0);
+                }
+            }
+        }
+        cp_async_wait<0>();
+    } else {
     I d_next = 0, p_next = 0;
     if (begin + lane < end) {
         d_next = ldg_idx(col_t + begin + lane);
         p_next = ldg_idx(t2csr + begin + lane);
     }
     for (int64_t b0 = begin; b0 < end; b0 += 32) {
-    const I d_cur = d_next, p_cur = p_next;
-    const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
-    d_next = p_next = 0;
-    if (b0 + 32 + lane < end) {
-        d_next = ldg_idx(col_t + b0 + 32 + lane);
-        p_next = ldg_idx(t2csr + b0 + 32 + lane);
-    }
-    for (int j0 = 0; j0 < nb; j0 += S * UNR) {
-        Vec16 gbuf[UNR][VPL], qb[UNR][VPL];
-        float2 pr[UNR][VPL];
-        bool ev[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int jj = j0 + u * S + sub;
-            ev[u] = jj < nb;
-            const int64_t d = static_cast<int64_t>(__shfl_sync(0xffffffffu, d_cur, jj & 31));
-            const int64_t p = static_cast<int64_t>(__shfl_sync(0xffffffffu, p_cur, jj & 31));
-            if (ev[u]) {
-#pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    if (!valid[k]) continue;
-                    const size_t off = static_cast<size_t>(lig + k * G) * 16;
-                    gbuf[u][k] = ldg_row16(gb + static_cast<size_t>(d) * row_bytes + off);
-                    if (MODE != ATTN_GAT) qb[u][k] = ldg_row16(a.q + static_cast<size_t>(d) * a.q_stride + off);
-                    pr[u][k] = __ldg(reinterpret_cast<const float2*>(pair) + p * a.heads + head[k]);
-                }
-            }
+        const I d_cur = d_next, p_cur = p_next;
+        const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
+        d_next = p_next = 0;
+        if (b0 + 32 + lane < end) {
+            d_next = ldg_idx(col_t + b0 + 32 + lane);
+            p_next = ldg_idx(t2csr + b0 + 32 + lane);
         }
+        for (int j0 = 0; j0 < nb; j0 += S * UNR) {
+            Vec16 gbuf[UNR][VPL], qb[UNR][VPL];
+            float2 pr[UNR][VPL];
+            bool ev[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            if (!ev[u]) continue;
+            for (int u = 0; u < UNR; ++u) {
+                const int jj = j0 + u * S + sub;
+                ev[u] = jj < nb;
+                const int64_t d = static_cast<int64_t>(__shfl_sync(0xffffffffu, d_cur, jj & 31));
+                const int64_t p = static_cast<int64_t>(__shfl_sync(0xffffffffu, p_cur, jj & 31));
+                if (ev[u]) {
 #pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-                if (!valid[k]) continue;
-                float g[EPV];
-                ElemTraits<T>::unpack(gbuf[u][k], g);
-                const float alpha = pr[u][k].x, gs = pr[u][k].y;
-#pragma unroll
-                for (int i = 0; i < EPV; ++i) accv[k][i] = fmaf(alpha, g[i], accv[k][i]);
-                if (MODE == ATTN_GAT) gss[k] += gs;
-                if (MODE != ATTN_GAT) {
-                    float qf[EPV];
-                    ElemTraits<T>::unpack(qb[u][k], qf);
-                    if (MODE == ATTN_GATV2) {
-#pragma unroll
-                        for (int i = 0; i < EPV; ++i) accv[k][i] = fmaf(gs * av[k][i], ((xl[k][i] + qf[i]) > 0.0f ? 1.0f : a.slope), accv[k][i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < EPV; ++i) acck[k][i] = fmaf(gs, qf[i], acck[k][i]);
+                    for (int k = 0; k < VPL; ++k) {
+                        if (!valid[k]) continue;
+                        const size_t off = static_cast<size_t>(lig + k * G) * 16;
+                        gbuf[u][k] = ldg_row16(gb + static_cast<size_t>(d) * row_bytes + off);
+                        if (MODE != ATTN_GAT) qb[u][k] = ldg_row16(a.q + static_cast<size_t>(d) * a.q_stride + off);
+                        pr[u][k] = __ldg(reinterpret_cast<const float2*>(pair) + p * a.heads + head[k]);
                     }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (ev[u]) consume(gbuf[u], qb[u], pr[u]);
         }
     }
-    }
+    }   // !STAGED
 #pragma unroll
     for (int o = G; o < 32; o <<= 1) {
 #pragma unroll
@@ -898,7 +1037,16 @@ int attn_backward_typed(const void* rowptr_, const void* col_, const void* rowpt
         unsigned blocks = static_cast<unsigned>(ceil_div(items, kAttnT / 32));
         if (MODE == ATTN_GATV2 && blocks > static_cast<unsigned>(gatt_rows)) blocks = static_cast<unsigned>(gatt_rows);   // persistent
 #define ATTN_DST(G_, V_) attn_bwd_dst_kernel<T, I, G_, V_, MODE, false><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, row_max, row_den, static_cast<const T*>(out), static_cast<const T*>(grad_out), pair, nullptr, static_cast<T*>(grad_q), grad_s_dst, gatt_part, n_rows, plan)
-        ATTN_BY_SHAPE(ATTN_DST);
+#define ATTN_DST_STAGED(G_) attn_bwd_dst_kernel<T, I, G_, 1, MODE, false, true><<<blocks, kAttnT, dst_stage, s>>>(rowptr, col, a, row_max, row_den, static_cast<const T*>(out), static_cast<const T*>(grad_out), pair, nullptr, static_cast<T*>(grad_q), grad_s_dst, gatt_part, n_rows, plan)
+        const size_t dst_stage = static_cast<size_t>(2) * 4 * kAttnT * ((MODE == ATTN_DOT ? 2 : 1) * 16 + 4);
+        if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
+            if (n_vec <= 8) ATTN_DST_STAGED(8);
+            else if (n_vec <= 16) ATTN_DST_STAGED(16);
+            else ATTN_DST_STAGED(32);
+        } else {
+            ATTN_BY_SHAPE(ATTN_DST);
+        }
+#undef ATTN_DST_STAGED
 #undef ATTN_DST
         B200MP_LAUNCH_CHECK();
         if (plan.n_long > 0) {
@@ -919,7 +1067,16 @@ int attn_backward_typed(const void* rowptr_, const void* col_, const void* rowpt
         const int64_t items = plan_t.n_chunks + n_src;
         const unsigned blocks = static_cast<unsigned>(ceil_div(items, kAttnT / 32));
 #define ATTN_SRC(G_, V_) attn_bwd_src_kernel<T, I, G_, V_, MODE><<<blocks, kAttnT, 0, s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
-        ATTN_BY_SHAPE(ATTN_SRC);
+#define ATTN_SRC_STAGED(G_) attn_bwd_src_kernel<T, I, G_, 1, MODE, true><<<blocks, kAttnT, src_stage, s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
+        const size_t src_stage = static_cast<size_t>(2) * 4 * kAttnT * ((MODE == ATTN_GAT ? 1 : 2) * 16 + 8);
+        if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
+            if (n_vec <= 8) ATTN_SRC_STAGED(8);
+            else if (n_vec <= 16) ATTN_SRC_STAGED(16);
+            else ATTN_SRC_STAGED(32);
+        } else {
+            ATTN_BY_SHAPE(ATTN_SRC);
+        }
+#undef ATTN_SRC_STAGED
 #undef ATTN_SRC
         B200MP_LAUNCH_CHECK();
         if (plan_t.n_long > 0) {
