@@ -46,6 +46,12 @@ def main():
     from pytorch_geometric_b200.nn import GATConv, RGCNConv, SAGEConv
     dev = torch.device("cuda", 0)
     todo = {int(c) for c in args.configs.split(",")}
+    if os.environ.get("B200MP_ATTN_STAGED") is not None:          # A/B switch of the cp.async-staged kernels (and the hit mask)
+        from pytorch_geometric_b200 import ops as _o
+        _o.set_option("attn_staged", int(os.environ["B200MP_ATTN_STAGED"]))
+    if os.environ.get("B200MP_MULTI_MASK") == "0":
+        from pytorch_geometric_b200 import ops as _o
+        _o.MULTI_HIT_MASK = False
 
     if 2 in todo:
         N, E, F = 10_000_000, 100_000_000, 256
@@ -131,10 +137,17 @@ def main():
             torch.autograd.backward(Fn.multi_aggregate(g, xg, aggrs), gouts)
 
         ms_fb = timed(step, args.steps)
+        from pytorch_geometric_b200 import ops as _ops
+        _ops.PROFILE.reset(True)                                # one more step with per-call events: the breakdown
+        step()
+        prof = {k: round(v["ms_total"], 3) for k, v in _ops.PROFILE.summary().items()}
+        _ops.PROFILE.reset(False)
         bytes_fwd = E * (F * 4 + 4) + N * F * 4 * len(aggrs) + (N + 1) * 4
         res = {"config": 6, "what": "multi-aggregation [mean,min,max,std], N=10M, E=100M, F=256, fp32",
                "fused_fwd_ms": ms_fused, "separate_fwd_ms": ms_sep,
-               "fused_fwd_algorithmic_GBps": bytes_fwd / (ms_fused * 1e-3) / 1e9, "fused_fwd_bwd_ms": ms_fb}
+               "fused_fwd_algorithmic_GBps": bytes_fwd / (ms_fused * 1e-3) / 1e9, "fused_fwd_bwd_ms": ms_fb,
+               "fwd_bwd_breakdown_ms": prof,
+               "staged": os.environ.get("B200MP_ATTN_STAGED", "1"), "hit_mask": os.environ.get("B200MP_MULTI_MASK", "1")}
         del x, xg, gouts
         torch.cuda.empty_cache()
         # segment form (what PNAConv / MultiAggregation see): materialised messages [E, 64] sorted by destination

@@ -240,10 +240,15 @@ int b200mp_column_sum(const void* x, float* out, float* partials, int64_t n_part
  * extremum is 0 if count_self_zero (ATen's scatter_reduce backward rule) -- what the backward divides by.
  * mean = sum / max(deg,1); var = sumsq / max(deg,1) - mean^2; std = sqrt(max(var,1e-5)), 0 where that is
  * <= sqrt(1e-5) (fused.py:319-323); empty rows give 0 everywhere.  Hub rows: long-row plan of
- * b200mp_csr_plan_* with partials of n_chunks * 6 * feat fp32. */
+ * b200mp_csr_plan_* with partials of n_chunks * 6 * feat fp32.
+ * hit_mask (nullable; gather mode, fp32, feat % 4 == 0, with a ties plane): uint8 [n_edges, feat / 4] in CSR edge
+ * order, bit i of byte (e, v) = x[col[e], 4v + i] equals the row's min, bit 4 + i = equals the row's max -- the
+ * comparison the backward needs, taken while the row's sources are still in L2, so that the backward reads one byte
+ * per edge and vector instead of the destination's min and max vectors (ask b200mp_multi_aggr_mask_supported). */
+int b200mp_multi_aggr_mask_supported(int64_t feat, int val_dtype, int segment_mode);
 int b200mp_multi_aggr_csr(const void* rowptr, const void* col, const void* x, void* out_sum, void* out_mean,
                           void* out_min, void* out_max, void* out_var, void* out_std, float* ties_min,
-                          float* ties_max, int64_t n_rows, int64_t n_src, int64_t feat, int count_self_zero,
+                          float* ties_max, void* hit_mask, int64_t n_rows, int64_t n_src, int64_t feat, int count_self_zero,
                           const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
                           int64_t n_chunks, int64_t chunk, float* partials, int idx_dtype, int val_dtype,
                           void* stream);
@@ -253,7 +258,10 @@ int b200mp_multi_aggr_csr(const void* rowptr, const void* col, const void* x, vo
  *   grad(x_e) = sum over the destinations d of the value:  term_a[d] + x * term_b[d]
  *               + [x == out_min[d]] * g_min[d] + [x == out_max[d]] * g_max[d].
  * segment_mode != 0: n_items = E messages, idx = dst_of_edge [E] (ptr unused), x / grad_x: [E, feat];
- * segment_mode == 0: n_items = n_src source rows, (ptr, idx) = transposed CSR (rowptr_t, col_t). */
+ * segment_mode == 0: n_items = n_src source rows, (ptr, idx) = transposed CSR (rowptr_t, col_t).
+ * hit_mask + t2csr (both nullable, gather mode only): the forward's hit bits and the CSR slot of every transposed
+ * slot; when given and supported they replace the reads of out_min / out_max (which must still be passed: shapes the
+ * masked kernel does not cover compare against them). */
 /* Elementwise prologue of the backward: folds the output gradients (nullable, [n_rows, feat] val_dtype) and
  * the saved mean / std / tie counts into term_a, term_b, g_min / ties_min, g_max / ties_max (fp32).
  * cnt = max(rowptr[i+1] - rowptr[i], 1); semi_grad drops the 2 x / cnt term of var / std (basic.py:106-110). */
@@ -265,8 +273,9 @@ int b200mp_multi_aggr_prepare_backward(const void* rowptr, const void* g_sum, co
                                        int64_t feat, int semi_grad, int idx_dtype, int val_dtype, void* stream);
 int b200mp_multi_aggr_backward(const void* ptr, const void* idx, const void* x, const float* term_a,
                                const float* term_b, const void* out_min, const float* g_min,
-                               const void* out_max, const float* g_max, void* grad_x, int64_t n_items,
-                               int64_t feat, int segment_mode, int idx_dtype, int val_dtype, void* stream);
+                               const void* out_max, const float* g_max, const void* hit_mask, const void* t2csr,
+                               void* grad_x, int64_t n_items, int64_t feat, int segment_mode, int idx_dtype,
+                               int val_dtype, void* stream);
 
 /* ------------------------------------------------------------------ fused GAT attention + aggregation
  * One sweep over the destination-sorted CSR per (node, head):

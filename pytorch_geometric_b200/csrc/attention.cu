@@ -71,21 +71,6 @@ __device__ __forceinline__ float head_sum(float v, int lph) {
     return v;
 }
 
-// cp.async (LDGSTS) into a LANE-PRIVATE shared-memory slot: the gathered row vector a lane will consume itself, fetched one
-// loop iteration ahead without holding registers (the issuing thread's own wait_group makes it visible to itself).
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // merge (m, s) softmax states: returns the two rescale factors
 __device__ __forceinline__ void merge_ms(float m1, float m2, float& M, float& c1, float& c2) {
     M = fmaxf(m1, m2);

@@ -28,11 +28,14 @@
 
 namespace b200mp {
 
+int get_option_attn_staged();   // core.cu: cp.async-staged gathers (default 1)
+
 enum { MA_SUM = 0, MA_MEAN, MA_MIN, MA_MAX, MA_VAR, MA_STD, MA_TIES_MIN, MA_TIES_MAX, MA_SLOTS };
 
 struct MultiOut {
     void* p[MA_SLOTS];      // [n_rows, feat]; slots 0..5 of the value dtype, the two tie planes fp32
     int self_zero;          // count the zero-initialised self as a tie (scatter semantics)
+    uint8_t* hit_mask;      // nullable [n_edges, feat / 4] (fp32 gather mode): bit i = x == row min, bit 4 + i = x == row max
 };
 
 // What the sweep has to carry per feature (compile-time: unused running values cost registers, and
@@ -230,6 +233,33 @@ multi_aggr_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const
         } else {
             ms_store_vec<T>(outs, static_cast<size_t>(row), row_bytes, voff, a, end - begin);
         }
+        if constexpr ((MODE & MA_NEED_TIES) != 0 && EPV == 4) {
+            // Second walk over the (short) row while its source rows are still in L2: one byte per (edge, vector) that
+            // says which of the four values attain the row's min / max.  The backward then reads 1 byte instead of the
+            // two 16-byte min / max vectors of the destination per edge (hub chunks: multi_aggr_mask_chunks_kernel).
+            if (outs.hit_mask && !is_chunk) {
+                constexpr int MUNR = 2;
+                for (int64_t e = begin; e < end; e += MUNR) {
+                    Vec16 buf[MUNR];
+#pragma unroll
+                    for (int u = 0; u < MUNR; ++u)
+                        if (e + u < end) {
+                            const int64_t c = GATHER ? static_cast<int64_t>(ldg_idx(col + e + u)) : (e + u);
+                            buf[u] = ldg_row16(xb + static_cast<size_t>(c) * row_bytes + voff);
+                        }
+#pragma unroll
+                    for (int u = 0; u < MUNR; ++u)
+                        if (e + u < end) {
+                            float f[EPV];
+                            ElemTraits<T>::unpack(buf[u], f);
+                            unsigned bits = 0;
+#pragma unroll
+                            for (int i = 0; i < EPV; ++i) bits |= (f[i] == a[i].mn ? 1u << i : 0u) | (f[i] == a[i].mx ? 16u << i : 0u);
+                            outs.hit_mask[static_cast<size_t>(e + u) * n_vec + v] = static_cast<uint8_t>(bits);
+                        }
+                }
+            }
+        }
     }
 }
 
@@ -295,6 +325,39 @@ multi_aggr_combine_kernel(const I* __restrict__ rowptr, MultiOut outs, int64_t f
     }
 }
 
+// Hit mask of the hub rows' edges (their min / max are only known after the combine): one lane group per chunk.
+template <typename I, int G>
+__global__ void __launch_bounds__(128)
+multi_aggr_mask_chunks_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const float* __restrict__ x,
+                              const float* __restrict__ out_min, const float* __restrict__ out_max,
+                              uint8_t* __restrict__ mask, int64_t n_rows, int n_vec, LongRowPlan plan) {
+    const int lig = threadIdx.x & (G - 1);
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    if (item >= plan.n_chunks) return;
+    int64_t row, begin, end;
+    bool is_chunk;
+    if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;
+    const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
+    for (int v = lig; v < n_vec; v += G) {
+        const size_t voff = static_cast<size_t>(v) * 16;
+        float mn[4], mx[4];
+        Vec16 t = {};
+        if (out_min) t = ldg_row16(reinterpret_cast<const char*>(out_min) + static_cast<size_t>(row) * row_bytes + voff);
+        ElemTraits<float>::unpack(t, mn);
+        if (out_max) t = ldg_row16(reinterpret_cast<const char*>(out_max) + static_cast<size_t>(row) * row_bytes + voff);
+        ElemTraits<float>::unpack(t, mx);
+        for (int64_t e = begin; e < end; ++e) {
+            float f[4];
+            ElemTraits<float>::unpack(ldg_row16(reinterpret_cast<const char*>(x) + static_cast<size_t>(ldg_idx(col + e)) * row_bytes + voff), f);
+            unsigned bits = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                bits |= ((out_min && f[i] == mn[i]) ? 1u << i : 0u) | ((out_max && f[i] == mx[i]) ? 16u << i : 0u);
+            mask[static_cast<size_t>(e) * n_vec + v] = static_cast<uint8_t>(bits);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- backward
 struct MultiGrad {
     const float* a;      // additive term              [n_dst, feat] or null
@@ -303,6 +366,8 @@ struct MultiGrad {
     const float* gmin;   // g_min / ties_min
     const void* mx;
     const float* gmax;
+    const uint8_t* hit_mask;   // gather mode, fp32: the forward's per-(edge, vector) hit bits in CSR edge order ...
+    const void* t2csr;         // ... and the CSR slot of every transposed slot (index dtype); replaces mn / mx
 };
 
 template <typename T>
@@ -449,6 +514,191 @@ multi_aggr_backward_vec_kernel(const I* __restrict__ ptr, const I* __restrict__ 
     }
 }
 
+// Warp-per-source-row form of the gather-mode backward for wide fp32 rows (n_vec in (16, 64]).  The per-destination rows
+// are fetched with cp.async into lane-private shared-memory slots one iteration ahead (the attention kernels' scheme,
+// attention.cu): the edge loop no longer alternates "index -> rows -> conditional rows" round trips, the next two
+// destinations' rows are already in flight while the tie-gradient rows of the current two are fetched.  Destination
+// indices are read 32 at a time (one coalesced load per lane) and broadcast with shuffles.
+// MASK: the forward's hit bits (one byte per edge and vector, CSR edge order, addressed through t2csr) replace the two
+// 16-byte min / max vectors of the destination: 2 rows + 1 byte per edge instead of 4 rows, plus the tie-gradient
+// vectors of the lanes that hit (on a degree-d destination every edge attains the extremum of ~1/d of the features).
+constexpr int kMbT = 128;
+template <typename I, int VPL, bool MASK>
+__global__ void __launch_bounds__(kMbT)
+multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict__ idx, const float* __restrict__ x,
+                                  MultiGrad g, float* __restrict__ grad_x, int64_t n_items, int n_vec) {
+    constexpr int D = 2, UNR = 2, NR = MASK ? 2 : 4;
+    extern __shared__ __align__(16) unsigned char mb_stage[];
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_items) return;
+    const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
+    bool valid[VPL];
+    float xv[VPL][4], acc[VPL][4];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        valid[k] = lane + k * 32 < n_vec;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[k][i] = acc[k][i] = 0.f;
+        if (valid[k])
+            ElemTraits<float>::unpack(ldg_stream16(reinterpret_cast<const char*>(x) + static_cast<size_t>(j) * row_bytes +
+                                                   static_cast<size_t>(lane + k * 32) * 16), xv[k]);
+    }
+    const int64_t begin = static_cast<int64_t>(ptr[j]);
+    const int deg = static_cast<int>(static_cast<int64_t>(ptr[j + 1]) - begin);
+    const int n_it = (deg + UNR - 1) / UNR;
+    unsigned char* base = mb_stage + static_cast<size_t>(threadIdx.x) * 16;
+    auto slot = [&](int d, int u, int r, int k) {
+        return base + static_cast<size_t>(((d * UNR + u) * NR + r) * VPL + k) * (kMbT * 16);
+    };
+    const char* rows[4] = {reinterpret_cast<const char*>(g.a), reinterpret_cast<const char*>(g.b),
+                           static_cast<const char*>(g.mn), static_cast<const char*>(g.mx)};
+    const I* t2csr = static_cast<const I*>(g.t2csr);
+    const bool use_mn = g.gmin != nullptr, use_mx = g.gmax != nullptr;
+    I i0 = 0, i1 = 0, p0 = 0, p1 = 0;
+    int cb = 0;
+    auto load_batch = [&](int b, I& ireg, I& preg) {
+        ireg = preg = 0;
+        if (b * 32 + lane < deg) {
+            ireg = ldg_idx(idx + begin + b * 32 + lane);
+            if (MASK) preg = ldg_idx(t2csr + begin + b * 32 + lane);
+        }
+    };
+    load_batch(0, i0, p0);
+    load_batch(1, i1, p1);
+    size_t off_cur[UNR] = {}, off_nxt[UNR] = {};
+    unsigned m_cur[UNR][VPL] = {}, m_nxt[UNR][VPL] = {};
+    auto issue = [&](int t) {
+        const int d = t & (D - 1);
+        const bool cur = ((t * UNR) >> 5) == cb;          // UNR divides 32: one iteration never straddles two index batches
+        const I ireg = cur ? i0 : i1, preg = cur ? p0 : p1;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int e = t * UNR + u;
+            const size_t off = static_cast<size_t>(__shfl_sync(0xffffffffu, ireg, e & 31)) * row_bytes;
+            size_t moff = 0;
+            if (MASK) moff = static_cast<size_t>(__shfl_sync(0xffffffffu, preg, e & 31)) * n_vec;
+            off_nxt[u] = off;
+            if (e < deg) {
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    if (!valid[k]) continue;
+                    const size_t o = off + static_cast<size_t>(lane + k * 32) * 16;
+#pragma unroll
+                    for (int r = 0; r < NR; ++r)
+                        if (rows[r]) cp_async16(slot(d, u, r, k), rows[r] + o);
+                    if (MASK) m_nxt[u][k] = __ldg(g.hit_mask + moff + lane + k * 32);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    if (n_it > 0) issue(0);
+    for (int t = 0; t < n_it; ++t) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            off_cur[u] = off_nxt[u];
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) m_cur[u][k] = m_nxt[u][k];
+        }
+        if (t + 1 < n_it) {
+            issue(t + 1);
+            if ((((t + 1) * UNR) >> 5) > cb) {
+                i0 = i1;
+                p0 = p1;
+                ++cb;
+                load_batch(cb + 1, i1, p1);
+            }
+        } else {
+            cp_async_commit();
+        }
+        cp_async_wait<1>();
+        const int d = t & (D - 1);
+        // first the hit tests of both destinations, so that the (frequent on low-degree destinations) tie-gradient loads
+        // of the two go out together
+        Vec16 gmn[UNR][VPL], gmx[UNR][VPL];
+        unsigned hits[UNR][VPL];                           // bits 0-3: value i attains the min, bits 4-7: the max
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                hits[u][k] = 0;
+                if (t * UNR + u >= deg || !valid[k]) continue;
+                if (MASK) {
+                    hits[u][k] = m_cur[u][k] & ((use_mn ? 0x0fu : 0u) | (use_mx ? 0xf0u : 0u));
+                } else {
+                    if (g.mn) {
+                        const Vec16 m = *reinterpret_cast<const Vec16*>(slot(d, u, 2, k));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) hits[u][k] |= xv[k][i] == __uint_as_float(m.w[i]) ? 1u << i : 0u;
+                    }
+                    if (g.mx) {
+                        const Vec16 m = *reinterpret_cast<const Vec16*>(slot(d, u, 3, k));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) hits[u][k] |= xv[k][i] == __uint_as_float(m.w[i]) ? 16u << i : 0u;
+                    }
+                }
+                const size_t o = off_cur[u] + static_cast<size_t>(lane + k * 32) * 16;
+                if (hits[u][k] & 0x0fu) gmn[u][k] = ldg_row16(reinterpret_cast<const char*>(g.gmin) + o);
+                if (hits[u][k] & 0xf0u) gmx[u][k] = ldg_row16(reinterpret_cast<const char*>(g.gmax) + o);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                if (t * UNR + u >= deg || !valid[k]) continue;
+                float tm[4] = {0.f, 0.f, 0.f, 0.f};
+                if (g.a) {
+                    const Vec16 r = *reinterpret_cast<const Vec16*>(slot(d, u, 0, k));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tm[i] = __uint_as_float(r.w[i]);
+                }
+                if (g.b) {
+                    const Vec16 r = *reinterpret_cast<const Vec16*>(slot(d, u, 1, k));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tm[i] = fmaf(xv[k][i], __uint_as_float(r.w[i]), tm[i]);
+                }
+                if (hits[u][k] & 0x0fu) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (hits[u][k] & (1u << i)) tm[i] += __uint_as_float(gmn[u][k].w[i]);
+                }
+                if (hits[u][k] & 0xf0u) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (hits[u][k] & (16u << i)) tm[i] += __uint_as_float(gmx[u][k].w[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[k][i] = __fadd_rn(acc[k][i], tm[i]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+        if (valid[k])
+            stg_stream16(reinterpret_cast<char*>(grad_x) + static_cast<size_t>(j) * row_bytes + static_cast<size_t>(lane + k * 32) * 16,
+                         ElemTraits<float>::pack(acc[k]));
+}
+
+template <typename I, int VPL, bool MASK>
+int multi_bwd_staged_launch(const I* ptr, const I* idx, const float* x, const MultiGrad& g, float* grad_x, int64_t n_items,
+                            int n_vec, cudaStream_t stream) {
+    // 2 stages x 2 destinations x (2 | 4) rows x VPL vectors of 16 bytes per thread
+    const size_t smem = static_cast<size_t>(2) * 2 * (MASK ? 2 : 4) * VPL * kMbT * 16;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        B200MP_CUDA(cudaFuncSetAttribute(multi_aggr_backward_staged_kernel<I, VPL, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+        attr_set = true;
+    }
+    multi_aggr_backward_staged_kernel<I, VPL, MASK><<<static_cast<unsigned>(ceil_div(n_items, kMbT / 32)), kMbT, smem, stream>>>(
+        ptr, idx, x, g, grad_x, n_items, n_vec);
+    B200MP_LAUNCH_CHECK();
+    return B200MP_OK;
+}
+
 template <typename T, typename I, bool GATHER, int MODE>
 void multi_launch_mode(const I* rowptr, const I* col, const T* x, const MultiOut& outs, int64_t n_rows, int n_vec,
                        const LongRowPlan& plan, cudaStream_t stream) {
@@ -491,6 +741,15 @@ int multi_launch(const I* rowptr, const I* col, const T* x, MultiOut outs, int64
     if (plan.n_long > 0) {
         multi_aggr_combine_kernel<T, I><<<static_cast<unsigned>(plan.n_long), 256, 0, stream>>>(rowptr, outs, feat, plan);
         B200MP_LAUNCH_CHECK();
+        if constexpr (GATHER && sizeof(T) == 4) {
+            if (outs.hit_mask) {
+                const int n_vec = static_cast<int>(row_bytes / 16);
+                multi_aggr_mask_chunks_kernel<I, 32><<<static_cast<unsigned>(ceil_div(plan.n_chunks, 128 / 32)), 128, 0, stream>>>(
+                    rowptr, col, reinterpret_cast<const float*>(x), static_cast<const float*>(outs.p[MA_MIN]),
+                    static_cast<const float*>(outs.p[MA_MAX]), outs.hit_mask, n_rows, n_vec, plan);
+                B200MP_LAUNCH_CHECK();
+            }
+        }
     }
     return B200MP_OK;
 }
@@ -530,7 +789,17 @@ int multi_bwd_typed(const void* ptr, const void* idx, const void* x, MultiGrad g
         if (segment)
             multi_bwd_vec_launch<I, true>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
                                           static_cast<const float*>(x), g, static_cast<float*>(grad_x), n_items, n_vec, stream);
-        else
+        else if (get_option_attn_staged() && n_vec > 16 && n_vec <= 64) {
+            const I* p = static_cast<const I*>(ptr);
+            const I* ix = static_cast<const I*>(idx);
+            const float* xf = static_cast<const float*>(x);
+            float* gx = static_cast<float*>(grad_x);
+            const bool masked = g.hit_mask != nullptr;
+            if (n_vec > 32) return masked ? multi_bwd_staged_launch<I, 2, true>(p, ix, xf, g, gx, n_items, n_vec, stream)
+                                          : multi_bwd_staged_launch<I, 2, false>(p, ix, xf, g, gx, n_items, n_vec, stream);
+            return masked ? multi_bwd_staged_launch<I, 1, true>(p, ix, xf, g, gx, n_items, n_vec, stream)
+                          : multi_bwd_staged_launch<I, 1, false>(p, ix, xf, g, gx, n_items, n_vec, stream);
+        } else
             multi_bwd_vec_launch<I, false>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
                                            static_cast<const float*>(x), g, static_cast<float*>(grad_x), n_items, n_vec, stream);
         B200MP_LAUNCH_CHECK();
@@ -567,7 +836,7 @@ using namespace b200mp;
 
 extern "C" int b200mp_multi_aggr_csr(const void* rowptr, const void* col, const void* x, void* out_sum,
                                      void* out_mean, void* out_min, void* out_max, void* out_var, void* out_std,
-                                     float* ties_min, float* ties_max, int64_t n_rows, int64_t n_src,
+                                     float* ties_min, float* ties_max, void* hit_mask, int64_t n_rows, int64_t n_src,
                                      int64_t feat, int count_self_zero, const int64_t* long_rows,
                                      const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks,
                                      int64_t chunk, float* partials, int idx_dtype, int val_dtype, void* stream) {
@@ -576,22 +845,35 @@ extern "C" int b200mp_multi_aggr_csr(const void* rowptr, const void* col, const 
     B200MP_CHECK_ARG(rowptr && (x || n_src == 0));
     B200MP_CHECK_ARG(n_long_rows >= 0 && n_chunks >= 0);
     B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && partials && chunk > 0));
-    MultiOut outs{{out_sum, out_mean, out_min, out_max, out_var, out_std, ties_min, ties_max}, count_self_zero != 0};
+    // the hit mask is a by-product of the tie-counting fp32 vector sweep in gather mode
+    B200MP_CHECK_ARG(!hit_mask || (col && val_dtype == B200MP_F32 && feat % 4 == 0 && (ties_min || ties_max) && aligned16(x)));
+    MultiOut outs{{out_sum, out_mean, out_min, out_max, out_var, out_std, ties_min, ties_max}, count_self_zero != 0,
+                  static_cast<uint8_t*>(hit_mask)};
     LongRowPlan plan{long_rows, chunk_ptr, n_long_rows, n_long_rows ? n_chunks : 0, chunk, partials,
                      nullptr, 0, 0, nullptr, 0};
     DISPATCH_T_I(multi_typed, rowptr, col, x, outs, n_rows, feat, plan, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int b200mp_multi_aggr_mask_supported(int64_t feat, int val_dtype, int segment_mode) {
+    return val_dtype == B200MP_F32 && !segment_mode && feat % 4 == 0 && feat > 64 && feat <= 256 && get_option_attn_staged();
+}
+
 extern "C" int b200mp_multi_aggr_backward(const void* ptr, const void* idx, const void* x, const float* term_a,
                                           const float* term_b, const void* out_min, const float* g_min,
-                                          const void* out_max, const float* g_max, void* grad_x,
-                                          int64_t n_items, int64_t feat, int segment_mode, int idx_dtype,
-                                          int val_dtype, void* stream) {
+                                          const void* out_max, const float* g_max, const void* hit_mask,
+                                          const void* t2csr, void* grad_x, int64_t n_items, int64_t feat,
+                                          int segment_mode, int idx_dtype, int val_dtype, void* stream) {
     B200MP_CHECK_ARG(n_items >= 0 && feat >= 0);
     if (n_items == 0 || feat == 0) return B200MP_OK;
     B200MP_CHECK_ARG(idx && x && grad_x && (segment_mode || ptr));
     B200MP_CHECK_ARG((!out_min || g_min) && (!out_max || g_max));
-    MultiGrad g{term_a, term_b, out_min, g_min, out_max, g_max};
+    B200MP_CHECK_ARG(!hit_mask || (t2csr && !segment_mode && val_dtype == B200MP_F32 && feat % 4 == 0));
+    // the mask is only read by the staged warp-per-row kernel; every other shape compares against out_min / out_max
+    const bool masked = hit_mask && b200mp_multi_aggr_mask_supported(feat, val_dtype, segment_mode) && aligned16(x) &&
+                        aligned16(grad_x) && aligned16(term_a) && aligned16(term_b) && aligned16(g_min) && aligned16(g_max);
+    MultiGrad g{term_a, term_b, masked ? nullptr : out_min, g_min, masked ? nullptr : out_max, g_max,
+                masked ? static_cast<const uint8_t*>(hit_mask) : nullptr, masked ? t2csr : nullptr};
+    B200MP_CHECK_ARG(masked || ((!g_min || out_min) && (!g_max || out_max)));
     DISPATCH_T_I(multi_bwd_typed, ptr, idx, x, g, grad_x, n_items, feat, segment_mode,
                  static_cast<cudaStream_t>(stream));
 }

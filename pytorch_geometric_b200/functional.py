@@ -347,12 +347,12 @@ class _MultiAggregate(torch.autograd.Function):
                                  count_self_zero=count_self_zero)
         ctx.where, ctx.names, ctx.gather, ctx.semi_grad = where, tuple(names), gather, semi_grad
         ctx.save_for_backward(x, res.get("min"), res.get("max"), res.get("ties_min"), res.get("ties_max"),
-                              res.get("mean"), res.get("std"))
+                              res.get("mean"), res.get("std"), res.get("hit_mask"))
         return tuple(res[n] for n in names)
 
     @staticmethod
     def backward(ctx, *grads):
-        x, omin, omax, tmin, tmax, mean, std = ctx.saved_tensors
+        x, omin, omax, tmin, tmax, mean, std, hit_mask = ctx.saved_tensors
         where = ctx.where
         g = {n: (None if gr is None else gr.to(x.dtype)) for n, gr in zip(ctx.names, grads)}
         if all(v is None for v in g.values()):
@@ -363,7 +363,8 @@ class _MultiAggregate(torch.autograd.Function):
         omax = omax if gmax is not None else None
         if ctx.gather:
             where.build_transpose()
-            gx = ops.multi_aggr_backward(where.rowptr_t, where.col_t, x, term_a, term_b, omin, gmin, omax, gmax, False)
+            gx = ops.multi_aggr_backward(where.rowptr_t, where.col_t, x, term_a, term_b, omin, gmin, omax, gmax, False,
+                                         hit_mask, None if hit_mask is None else where.t2csr)
         else:
             gx = ops.multi_aggr_backward(None, where[1], x, term_a, term_b, omin, gmin, omax, gmax, True)
         return gx, None, None, None, None

@@ -644,6 +644,7 @@ def column_sum(x: Tensor) -> Tensor:
 
 
 MULTI_AGGRS = ("sum", "mean", "min", "max", "var", "std")
+MULTI_HIT_MASK = True       # emit the forward's hit bits for the backward (A/B switch for benchmarks)
 
 
 def multi_aggr_csr(rowptr: Tensor, col: Optional[Tensor], x: Tensor, n_rows: int, want, plan=None,
@@ -666,10 +667,14 @@ def multi_aggr_csr(rowptr: Tensor, col: Optional[Tensor], x: Tensor, n_rows: int
         for name in ("min", "max"):
             if name in res:
                 res["ties_" + name] = torch.empty(n_rows, F, dtype=torch.float32, device=x.device)
+    # hit bits for the backward (one byte per edge and 16-byte vector): only where its masked kernel exists
+    if (MULTI_HIT_MASK and with_ties and col is not None and ("ties_min" in res or "ties_max" in res)
+            and lib().b200mp_multi_aggr_mask_supported(F, _vdt(x), 0)):
+        res["hit_mask"] = torch.empty(col.numel() * (F // 4), dtype=torch.uint8, device=x.device)
     pargs, _ = _plan_args(plan, 6 * F, x.device)
-    _timed("multi_aggr_csr", 2 if pargs[2] else 1, lib().b200mp_multi_aggr_csr, _p(rowptr), _p(col), _p(x),
-           *[_p(res.get(n)) for n in MULTI_AGGRS], _p(res.get("ties_min")), _p(res.get("ties_max")), n_rows,
-           x.size(0), F, int(bool(count_self_zero)), *pargs, it, _vdt(x), _stream())
+    _timed("multi_aggr_csr", (3 if "hit_mask" in res else 2) if pargs[2] else 1, lib().b200mp_multi_aggr_csr, _p(rowptr),
+           _p(col), _p(x), *[_p(res.get(n)) for n in MULTI_AGGRS], _p(res.get("ties_min")), _p(res.get("ties_max")),
+           _p(res.get("hit_mask")), n_rows, x.size(0), F, int(bool(count_self_zero)), *pargs, it, _vdt(x), _stream())
     return res
 
 
@@ -700,10 +705,16 @@ def multi_aggr_prepare_backward(rowptr: Tensor, grads: dict, mean: Optional[Tens
 
 def multi_aggr_backward(ptr: Optional[Tensor], idx: Tensor, x: Tensor, term_a: Optional[Tensor],
                         term_b: Optional[Tensor], out_min: Optional[Tensor], g_min: Optional[Tensor],
-                        out_max: Optional[Tensor], g_max: Optional[Tensor], segment_mode: bool) -> Tensor:
+                        out_max: Optional[Tensor], g_max: Optional[Tensor], segment_mode: bool,
+                        hit_mask: Optional[Tensor] = None, t2csr: Optional[Tensor] = None) -> Tensor:
     """grad wrt the message values (see b200mp_multi_aggr_backward).  segment_mode: idx = destination of
-    every message; otherwise (ptr, idx) is the transposed CSR and x the [n_src, F] source matrix."""
-    _cuda(ptr, idx, x, term_a, term_b, out_min, g_min, out_max, g_max)
+    every message; otherwise (ptr, idx) is the transposed CSR and x the [n_src, F] source matrix.
+    hit_mask / t2csr: the forward's hit bits (multi_aggr_csr's 'hit_mask') and the CSR slot of every transposed slot."""
+    _cuda(ptr, idx, x, term_a, term_b, out_min, g_min, out_max, g_max, hit_mask, t2csr)
+    if hit_mask is not None:
+        if t2csr is None or segment_mode or t2csr.dtype != idx.dtype:
+            raise ValueError("hit_mask needs gather mode and t2csr of the index dtype")
+        t2csr = t2csr.contiguous()
     x = x.contiguous()
 
     def f32(t):
@@ -715,7 +726,7 @@ def multi_aggr_backward(ptr: Optional[Tensor], idx: Tensor, x: Tensor, term_a: O
     gx = torch.empty_like(x)
     it = _idt(idx) if segment_mode else _same_idx(ptr, idx)
     _timed("multi_aggr_backward", 1, lib().b200mp_multi_aggr_backward, _p(ptr), _p(idx), _p(x), _p(term_a),
-           _p(term_b), _p(out_min), _p(g_min), _p(out_max), _p(g_max), _p(gx), x.size(0), x.size(1),
+           _p(term_b), _p(out_min), _p(g_min), _p(out_max), _p(g_max), _p(hit_mask), _p(t2csr), _p(gx), x.size(0), x.size(1),
            int(bool(segment_mode)), it, _vdt(x), _stream())
     return gx
 

@@ -112,12 +112,14 @@ def test_fused_errors():
 
 @pytest.mark.parametrize("F,dtype,chunk", [(1, torch.float32, 512), (7, torch.float32, 512), (64, torch.float32, 16),
                                            (256, torch.float32, 16), (132, torch.float32, 512),
+                                           (96, torch.float32, 512), (128, torch.float32, 16),
                                            (64, torch.bfloat16, 16), (8, torch.bfloat16, 512)])
 def test_gather_mode_vs_oracle(F, dtype, chunk):
     """Graph form: out_k[i] = aggr_k over x[src] of the in-edges of i; hub rows chunked when chunk = 16."""
     rng = np.random.default_rng(F + chunk)
     N, E = 700, 20000
     src = rng.integers(0, N, size=E)
+    src[rng.random(E) < 0.02] = 3                                   # one hub SOURCE (~400 out-edges): the backward's index batches
     dst = ((rng.random(E) ** 3) * (N - 5)).astype(np.int64)        # skewed, last rows empty
     x = rng.standard_normal((N, F)).astype(np.float32)
     x[rng.random((N, F)) < 0.2] = 0.0                               # post-ReLU zeros -> ties at 0
