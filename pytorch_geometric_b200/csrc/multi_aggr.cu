@@ -150,22 +150,24 @@ __device__ __forceinline__ void ms_store_vec(const MultiOut& o, size_t row, size
             put(MA_STD);
         }
     }
-    // tie planes are fp32 whatever T is
+    // tie planes are fp32 whatever T is: EPV floats = EPV / 4 16-byte stores
     const size_t e0 = row * (row_bytes / sizeof(T)) + voff / sizeof(T);
-    if (o.p[MA_TIES_MIN]) {
+    auto put_ties = [&](int slot, bool is_min) {
+        float t[EPV];
 #pragma unroll
         for (int i = 0; i < EPV; ++i) {
-            const float mn = deg == 0 ? 0.f : a[i].mn;
-            static_cast<float*>(o.p[MA_TIES_MIN])[e0 + i] = a[i].cmn + ((o.self_zero && mn == 0.f) ? 1.f : 0.f);
+            const float ext = deg == 0 ? 0.f : (is_min ? a[i].mn : a[i].mx);
+            t[i] = (is_min ? a[i].cmn : a[i].cmx) + ((o.self_zero && ext == 0.f) ? 1.f : 0.f);
         }
-    }
-    if (o.p[MA_TIES_MAX]) {
+        float* dst = static_cast<float*>(o.p[slot]) + e0;
 #pragma unroll
-        for (int i = 0; i < EPV; ++i) {
-            const float mx = deg == 0 ? 0.f : a[i].mx;
-            static_cast<float*>(o.p[MA_TIES_MAX])[e0 + i] = a[i].cmx + ((o.self_zero && mx == 0.f) ? 1.f : 0.f);
+        for (int q = 0; q < EPV / 4; ++q) {
+            const float t4[4] = {t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]};
+            stg_stream16(dst + 4 * q, ElemTraits<float>::pack(t4));
         }
-    }
+    };
+    if (o.p[MA_TIES_MIN]) put_ties(MA_TIES_MIN, true);
+    if (o.p[MA_TIES_MAX]) put_ties(MA_TIES_MAX, false);
 }
 
 // Resident 128-thread CTAs per SM the register budget is capped for (occupancy is what hides the
@@ -443,9 +445,80 @@ multi_aggr_prepare_kernel(const I* __restrict__ rowptr, MultiPrep p, int64_t n_r
     if (p.gmax) p.gmax[i] = ld(p.g_max) / fmaxf(p.ties_max[i], 1.f);
 }
 
+// fp32 rows of whole 16-byte vectors: one vector per thread, 16-byte streaming loads / stores (the scalar form spends its
+// time on a 64-bit division and 4-byte accesses per element: 38 ms for 12 planes of 10 GB, this one is bound by the bytes).
+template <typename I>
+__global__ void __launch_bounds__(256)
+multi_aggr_prepare_vec_kernel(const I* __restrict__ rowptr, MultiPrep p, int64_t n_total, unsigned n_vec, bool semi_grad) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const int64_t row = n_total < (int64_t{1} << 32) ? static_cast<int64_t>(static_cast<unsigned>(i) / n_vec) : i / n_vec;
+    const int64_t deg = static_cast<int64_t>(rowptr[row + 1]) - static_cast<int64_t>(rowptr[row]);
+    const float cnt = static_cast<float>(deg < 1 ? 1 : deg);
+    const size_t off = static_cast<size_t>(i) * 16;
+    auto ld = [&](const void* q, float (&f)[4]) { ElemTraits<float>::unpack(ldg_stream16(static_cast<const char*>(q) + off), f); };
+    auto st = [&](float* q, const float (&f)[4]) { stg_stream16(reinterpret_cast<char*>(q) + off, ElemTraits<float>::pack(f)); };
+    float t[4], u[4];
+    if (p.term_a) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.g_sum) ld(p.g_sum, a);
+        if (p.g_mean) {
+            ld(p.g_mean, t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] += t[k] / cnt;
+        }
+        if (p.g_var || p.g_std) {
+            float gv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.g_var) ld(p.g_var, gv);
+            if (p.g_std) {
+                ld(p.std, t);
+                ld(p.g_std, u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (t[k] > 0.f) gv[k] += u[k] * 0.5f / t[k];
+            }
+            ld(p.mean, t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a[k] -= 2.f * gv[k] * t[k] / cnt;
+                u[k] = semi_grad ? 0.f : 2.f * gv[k] / cnt;
+            }
+            if (p.term_b) st(p.term_b, u);
+        }
+        st(p.term_a, a);
+    }
+    if (p.gmin) {
+        ld(p.g_min, t);
+        ld(p.ties_min, u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = t[k] / fmaxf(u[k], 1.f);
+        st(p.gmin, t);
+    }
+    if (p.gmax) {
+        ld(p.g_max, t);
+        ld(p.ties_max, u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = t[k] / fmaxf(u[k], 1.f);
+        st(p.gmax, t);
+    }
+}
+
 template <typename T, typename I>
 int multi_prep_typed(const void* rowptr, MultiPrep p, int64_t n_rows, int64_t feat, int semi_grad, cudaStream_t stream) {
     const int64_t n = n_rows * feat;
+    if constexpr (sizeof(T) == 4) {
+        bool vec_ok = feat % 4 == 0;
+        for (const void* q : {p.g_sum, p.g_mean, p.g_var, p.g_std, p.g_min, p.g_max, p.mean, p.std, static_cast<const void*>(p.ties_min),
+                              static_cast<const void*>(p.ties_max), static_cast<const void*>(p.term_a), static_cast<const void*>(p.term_b),
+                              static_cast<const void*>(p.gmin), static_cast<const void*>(p.gmax)})
+            vec_ok = vec_ok && aligned16(q);
+        if (vec_ok) {
+            multi_aggr_prepare_vec_kernel<I><<<static_cast<unsigned>(ceil_div(n / 4, 256)), 256, 0, stream>>>(
+                static_cast<const I*>(rowptr), p, n / 4, static_cast<unsigned>(feat / 4), semi_grad != 0);
+            B200MP_LAUNCH_CHECK();
+            return B200MP_OK;
+        }
+    }
     multi_aggr_prepare_kernel<T, I><<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(
         static_cast<const I*>(rowptr), p, n_rows, feat, semi_grad != 0);
     B200MP_LAUNCH_CHECK();
@@ -699,10 +772,145 @@ int multi_bwd_staged_launch(const I* ptr, const I* idx, const float* x, const Mu
     return B200MP_OK;
 }
 
+// ---------------------------------------------------------------- warp-per-row forward with staged gathers
+// Walk `deg` gathered rows (x[col[begin + e]], e ascending) with one warp: lane owns vectors lane, lane + 32 (VPL of
+// them).  Source indices come 32 at a time (one coalesced load per lane, broadcast by shuffle); the row vectors are
+// fetched by cp.async into lane-private shared-memory slots UNR rows per stage, stage t + 1 in flight while stage t
+// is consumed.  consume(e, k, vec) is called in edge order, so sums keep the CSR order of the register form.
+constexpr int kMfT = 128, kMfUnr = 4;
+template <typename I, int VPL, typename F>
+__device__ __forceinline__ void staged_row_walk(const I* __restrict__ col, int64_t begin, int deg, const char* xb,
+                                                size_t row_bytes, const bool (&valid)[VPL], int lane,
+                                                unsigned char* base, F&& consume) {
+    constexpr int D = 2, UNR = kMfUnr;
+    auto slot = [&](int d, int u, int k) { return base + static_cast<size_t>((d * UNR + u) * VPL + k) * (kMfT * 16); };
+    const int n_it = (deg + UNR - 1) / UNR;
+    I i0 = 0, i1 = 0;
+    int cb = 0;
+    if (lane < deg) i0 = ldg_idx(col + begin + lane);
+    if (32 + lane < deg) i1 = ldg_idx(col + begin + 32 + lane);
+    auto issue = [&](int t) {
+        const int d = t & (D - 1);
+        const I ireg = ((t * UNR) >> 5) == cb ? i0 : i1;   // UNR divides 32: a stage never straddles two index batches
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int e = t * UNR + u;
+            const size_t off = static_cast<size_t>(__shfl_sync(0xffffffffu, ireg, e & 31)) * row_bytes;
+            if (e < deg) {
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+                    if (valid[k]) cp_async16(slot(d, u, k), xb + off + static_cast<size_t>(lane + k * 32) * 16);
+            }
+        }
+        cp_async_commit();
+    };
+    if (n_it > 0) issue(0);
+    for (int t = 0; t < n_it; ++t) {
+        if (t + 1 < n_it) {
+            issue(t + 1);
+            if ((((t + 1) * UNR) >> 5) > cb) {
+                i0 = i1;
+                ++cb;
+                i1 = 0;
+                if ((cb + 1) * 32 + lane < deg) i1 = ldg_idx(col + begin + (cb + 1) * 32 + lane);
+            }
+        } else {
+            cp_async_commit();
+        }
+        cp_async_wait<1>();
+        const int d = t & (D - 1);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int e = t * UNR + u;
+            if (e < deg) {
+#pragma unroll
+                for (int k = 0; k < VPL; ++k)
+                    if (valid[k]) consume(e, k, *reinterpret_cast<const Vec16*>(slot(d, u, k)));
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <typename I, int VPL, int MODE>
+__global__ void __launch_bounds__(kMfT)
+multi_aggr_staged_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const float* __restrict__ x,
+                         MultiOut outs, int64_t n_rows, int n_vec, LongRowPlan plan) {
+    extern __shared__ __align__(16) unsigned char mf_stage[];
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    int64_t row, begin, end;
+    bool is_chunk;
+    if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;
+    const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
+    const int64_t feat = static_cast<int64_t>(n_vec) * 4;
+    const char* xb = reinterpret_cast<const char*>(x);
+    unsigned char* base = mf_stage + static_cast<size_t>(threadIdx.x) * 16;
+    const int deg = static_cast<int>(end - begin);
+    bool valid[VPL];
+    MultiState a[VPL][4];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        valid[k] = lane + k * 32 < n_vec;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ms_init(a[k][i]);
+    }
+    staged_row_walk<I, VPL>(col, begin, deg, xb, row_bytes, valid, lane, base, [&](int, int k, const Vec16& v) {
+        float f[4];
+        ElemTraits<float>::unpack(v, f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ms_push<MODE>(a[k][i], f[i]);
+    });
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        if (!valid[k]) continue;
+        const int v = lane + k * 32;
+        if (is_chunk) {
+            float* pb = plan.partials + static_cast<size_t>(item) * 6 * feat + static_cast<size_t>(v) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                pb[i] = a[k][i].s;
+                pb[feat + i] = a[k][i].q;
+                pb[2 * feat + i] = a[k][i].mn;
+                pb[3 * feat + i] = a[k][i].mx;
+                pb[4 * feat + i] = a[k][i].cmn;
+                pb[5 * feat + i] = a[k][i].cmx;
+            }
+        } else {
+            ms_store_vec<float>(outs, static_cast<size_t>(row), row_bytes, static_cast<size_t>(v) * 16, a[k], end - begin);
+        }
+    }
+    if constexpr ((MODE & MA_NEED_TIES) != 0) {
+        // second walk while the row's sources are still in L2: the hit bits for the backward (see MultiOut::hit_mask)
+        if (outs.hit_mask && !is_chunk) {
+            uint8_t* mrow = outs.hit_mask + static_cast<size_t>(begin) * n_vec + lane;
+            staged_row_walk<I, VPL>(col, begin, deg, xb, row_bytes, valid, lane, base, [&](int e, int k, const Vec16& v) {
+                float f[4];
+                ElemTraits<float>::unpack(v, f);
+                unsigned bits = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bits |= (f[i] == a[k][i].mn ? 1u << i : 0u) | (f[i] == a[k][i].mx ? 16u << i : 0u);
+                mrow[static_cast<size_t>(e) * n_vec + k * 32] = static_cast<uint8_t>(bits);
+            });
+        }
+    }
+}
+
 template <typename T, typename I, bool GATHER, int MODE>
 void multi_launch_mode(const I* rowptr, const I* col, const T* x, const MultiOut& outs, int64_t n_rows, int n_vec,
                        const LongRowPlan& plan, cudaStream_t stream) {
     const int64_t items = plan.n_chunks + n_rows;
+    if constexpr (GATHER && sizeof(T) == 4) {
+        if (get_option_attn_staged() && n_vec > 16 && n_vec <= 64) {
+            const unsigned blocks = static_cast<unsigned>(ceil_div(items, kMfT / 32));
+            const float* xf = reinterpret_cast<const float*>(x);
+            if (n_vec > 32)
+                multi_aggr_staged_kernel<I, 2, MODE><<<blocks, kMfT, 2 * kMfUnr * 2 * kMfT * 16, stream>>>(rowptr, col, xf, outs, n_rows, n_vec, plan);
+            else
+                multi_aggr_staged_kernel<I, 1, MODE><<<blocks, kMfT, 2 * kMfUnr * 1 * kMfT * 16, stream>>>(rowptr, col, xf, outs, n_rows, n_vec, plan);
+            return;
+        }
+    }
 #define B200MP_MA(G_)                                                                                            \
     multi_aggr_kernel<T, I, G_, GATHER, MODE><<<static_cast<unsigned>(ceil_div(items, 128 / G_)), 128, 0, stream>>>( \
         rowptr, col, x, outs, n_rows, n_vec, plan)
@@ -789,7 +997,9 @@ int multi_bwd_typed(const void* ptr, const void* idx, const void* x, MultiGrad g
         if (segment)
             multi_bwd_vec_launch<I, true>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
                                           static_cast<const float*>(x), g, static_cast<float*>(grad_x), n_items, n_vec, stream);
-        else if (get_option_attn_staged() && n_vec > 16 && n_vec <= 64) {
+        else if (g.hit_mask && n_vec > 16 && n_vec <= 64) {
+            // (without the mask the staged form holds 4 rows x 2 destinations x 2 stages per thread = 64 KB per CTA; 12 warps
+            //  per SM ran the sweep at 113 ms against 73 ms for the register form below at 24 -- measured, r2c_multi_*.json)
             const I* p = static_cast<const I*>(ptr);
             const I* ix = static_cast<const I*>(idx);
             const float* xf = static_cast<const float*>(x);

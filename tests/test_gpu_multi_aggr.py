@@ -132,6 +132,10 @@ def test_gather_mode_vs_oracle(F, dtype, chunk):
         assert g.plan.n_long > 0
     xt = cu(x).to(dtype).requires_grad_()
     outs = Fn.multi_aggregate(g, xt, aggrs)
+    with torch.no_grad():                                           # inference sweeps (no tie counts, no hit mask): same values
+        for sub in (aggrs, ["min", "max"], ["sum", "std"]):
+            for name, o in zip(sub, Fn.multi_aggregate(g, xt, sub)):
+                assert torch.equal(o, outs[aggrs.index(name)]), name
     deg = np.bincount(dst, minlength=N)
     short = deg <= chunk
     if dtype == torch.float32:
