@@ -49,6 +49,9 @@ def main():
     if os.environ.get("B200MP_ATTN_STAGED") is not None:          # A/B switch of the cp.async-staged kernels (and the hit mask)
         from pytorch_geometric_b200 import ops as _o
         _o.set_option("attn_staged", int(os.environ["B200MP_ATTN_STAGED"]))
+    if os.environ.get("B200MP_MULTI_TUNE"):
+        from pytorch_geometric_b200 import ops as _o
+        _o.set_option("multi_tune", int(os.environ["B200MP_MULTI_TUNE"]))
     if os.environ.get("B200MP_MULTI_MASK") == "0":
         from pytorch_geometric_b200 import ops as _o
         _o.MULTI_HIT_MASK = False
@@ -147,7 +150,8 @@ def main():
                "fused_fwd_ms": ms_fused, "separate_fwd_ms": ms_sep,
                "fused_fwd_algorithmic_GBps": bytes_fwd / (ms_fused * 1e-3) / 1e9, "fused_fwd_bwd_ms": ms_fb,
                "fwd_bwd_breakdown_ms": prof,
-               "staged": os.environ.get("B200MP_ATTN_STAGED", "1"), "hit_mask": os.environ.get("B200MP_MULTI_MASK", "1")}
+               "staged": os.environ.get("B200MP_ATTN_STAGED", "1"), "hit_mask": os.environ.get("B200MP_MULTI_MASK", "1"),
+               "multi_tune": os.environ.get("B200MP_MULTI_TUNE", "6")}
         del x, xg, gouts
         torch.cuda.empty_cache()
         # segment form (what PNAConv / MultiAggregation see): materialised messages [E, 64] sorted by destination

@@ -56,6 +56,8 @@ static int g_spmm_tune = 0;
 int get_option_spmm_tune() { return g_spmm_tune; }
 static int g_attn_staged = 1;   // cp.async-staged attention forward (csrc/attention.cu); 0 = register-staged loop
 int get_option_attn_staged() { return g_attn_staged; }
+static int g_multi_tune = 6;    // resident CTAs per SM the masked multi-aggregation sweep is compiled for (5 | 6), multi_aggr.cu
+int get_option_multi_tune() { return g_multi_tune; }
 
 // Work counters of the persistent kernels: a small device-resident pool, one slot per launch in
 // round-robin order, zeroed on the launching stream right before the kernel (so concurrent
@@ -94,6 +96,11 @@ extern "C" int b200mp_set_option(const char* name, int value) {
     }
     if (strcmp(name, "spmm_tune") == 0) {
         b200mp::g_spmm_tune = value;
+        return B200MP_OK;
+    }
+    if (strcmp(name, "multi_tune") == 0) {
+        if (value != 5 && value != 6) return B200MP_ERR_INVALID_ARG;
+        b200mp::g_multi_tune = value;
         return B200MP_OK;
     }
     if (strcmp(name, "attn_staged") == 0) {

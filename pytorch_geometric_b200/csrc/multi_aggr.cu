@@ -29,6 +29,7 @@
 namespace b200mp {
 
 int get_option_attn_staged();   // core.cu: cp.async-staged gathers (default 1)
+int get_option_multi_tune();    // core.cu: resident CTAs per SM of the masked sweep (5 | 6)
 
 enum { MA_SUM = 0, MA_MEAN, MA_MIN, MA_MAX, MA_VAR, MA_STD, MA_TIES_MIN, MA_TIES_MAX, MA_SLOTS };
 
@@ -235,33 +236,81 @@ multi_aggr_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const
         } else {
             ms_store_vec<T>(outs, static_cast<size_t>(row), row_bytes, voff, a, end - begin);
         }
-        if constexpr ((MODE & MA_NEED_TIES) != 0 && EPV == 4) {
-            // Second walk over the (short) row while its source rows are still in L2: one byte per (edge, vector) that
-            // says which of the four values attain the row's min / max.  The backward then reads 1 byte instead of the
-            // two 16-byte min / max vectors of the destination per edge (hub chunks: multi_aggr_mask_chunks_kernel).
-            if (outs.hit_mask && !is_chunk) {
-                constexpr int MUNR = 2;
-                for (int64_t e = begin; e < end; e += MUNR) {
-                    Vec16 buf[MUNR];
+    }
+}
+
+// Training sweep with hit bits (gather mode, fp32, 16 < n_vec <= 64): one WARP per work item.
+//   pass 1  the register-form walk above with the four running values s, q, mn, mx (no tie counters: 64 instead of 80
+//           registers), and every 16-byte vector it consumes is also parked in a lane-private shared-memory slot
+//           (the first kKeep edges of the row: 98 % of the rows of a mean-degree-10 graph fit);
+//   pass 2  the row's min / max are final: walk the parked vectors (re-gather only edges >= kKeep), emit one byte per
+//           (edge, vector) -- bit i: value i attains the min, bit 4 + i: the max -- and count the bits = the tie counts.
+// Hub chunks are not handled here: they go through multi_aggr_kernel<kModeAllTies> (launched over the chunk items only);
+// their min / max are final after the combine and their bits are written by multi_aggr_mask_chunks_kernel.  A first version re-gathered every row in pass 2 and cost +28 ms at the 100 M-edge
+// shape; parking the vectors makes pass 2 a shared-memory walk.
+constexpr int kKeep = 16;
+template <typename I, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+multi_aggr_masked_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const float* __restrict__ x,
+                         MultiOut outs, int64_t n_rows, int n_vec, LongRowPlan plan) {
+    constexpr int UNR = 4;
+    constexpr int kSums = MA_NEED_SUM | MA_NEED_SQ | MA_NEED_MM;
+    __shared__ Vec16 keep[kKeep][128];
+    const int lane = threadIdx.x & 31;
+    const int64_t item = plan.n_chunks + ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);   // rows only
+    int64_t row, begin, end;
+    bool is_chunk;
+    if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;
+    const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
+    const char* xb = reinterpret_cast<const char*>(x);
+    for (int v = lane; v < n_vec; v += 32) {
+        MultiState a[4];
 #pragma unroll
-                    for (int u = 0; u < MUNR; ++u)
-                        if (e + u < end) {
-                            const int64_t c = GATHER ? static_cast<int64_t>(ldg_idx(col + e + u)) : (e + u);
-                            buf[u] = ldg_row16(xb + static_cast<size_t>(c) * row_bytes + voff);
-                        }
+        for (int i = 0; i < 4; ++i) ms_init(a[i]);
+        const size_t voff = static_cast<size_t>(v) * 16;
+        for (int64_t e = begin; e < end; e += UNR) {
+            Vec16 buf[UNR];
 #pragma unroll
-                    for (int u = 0; u < MUNR; ++u)
-                        if (e + u < end) {
-                            float f[EPV];
-                            ElemTraits<T>::unpack(buf[u], f);
-                            unsigned bits = 0;
+            for (int u = 0; u < UNR; ++u)
+                if (e + u < end) buf[u] = ldg_row16(xb + static_cast<size_t>(ldg_idx(col + e + u)) * row_bytes + voff);
 #pragma unroll
-                            for (int i = 0; i < EPV; ++i) bits |= (f[i] == a[i].mn ? 1u << i : 0u) | (f[i] == a[i].mx ? 16u << i : 0u);
-                            outs.hit_mask[static_cast<size_t>(e + u) * n_vec + v] = static_cast<uint8_t>(bits);
-                        }
+            for (int u = 0; u < UNR; ++u) {
+                if (e + u < end) {
+                    float f[4];
+                    ElemTraits<float>::unpack(buf[u], f);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ms_push<kSums>(a[i], f[i]);
+                    if (e + u - begin < kKeep) keep[e + u - begin][threadIdx.x] = buf[u];
                 }
             }
         }
+        uint8_t* mrow = outs.hit_mask + static_cast<size_t>(begin) * n_vec + v;
+        const int deg = static_cast<int>(end - begin);
+        auto emit = [&](int e, const Vec16& vec) {
+            float f[4];
+            ElemTraits<float>::unpack(vec, f);
+            unsigned bits = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool hmn = f[i] == a[i].mn, hmx = f[i] == a[i].mx;
+                a[i].cmn += hmn ? 1.f : 0.f;
+                a[i].cmx += hmx ? 1.f : 0.f;
+                bits |= (hmn ? 1u << i : 0u) | (hmx ? 16u << i : 0u);
+            }
+            mrow[static_cast<size_t>(e) * n_vec] = static_cast<uint8_t>(bits);
+        };
+        const int kept = deg < kKeep ? deg : kKeep;
+        for (int e = 0; e < kept; ++e) emit(e, keep[e][threadIdx.x]);
+        for (int e = kKeep; e < deg; e += UNR) {
+            Vec16 buf[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (e + u < deg) buf[u] = ldg_row16(xb + static_cast<size_t>(ldg_idx(col + begin + e + u)) * row_bytes + voff);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (e + u < deg) emit(e + u, buf[u]);
+        }
+        ms_store_vec<float>(outs, static_cast<size_t>(row), row_bytes, voff, a, end - begin);
     }
 }
 
@@ -772,145 +821,10 @@ int multi_bwd_staged_launch(const I* ptr, const I* idx, const float* x, const Mu
     return B200MP_OK;
 }
 
-// ---------------------------------------------------------------- warp-per-row forward with staged gathers
-// Walk `deg` gathered rows (x[col[begin + e]], e ascending) with one warp: lane owns vectors lane, lane + 32 (VPL of
-// them).  Source indices come 32 at a time (one coalesced load per lane, broadcast by shuffle); the row vectors are
-// fetched by cp.async into lane-private shared-memory slots UNR rows per stage, stage t + 1 in flight while stage t
-// is consumed.  consume(e, k, vec) is called in edge order, so sums keep the CSR order of the register form.
-constexpr int kMfT = 128, kMfUnr = 4;
-template <typename I, int VPL, typename F>
-__device__ __forceinline__ void staged_row_walk(const I* __restrict__ col, int64_t begin, int deg, const char* xb,
-                                                size_t row_bytes, const bool (&valid)[VPL], int lane,
-                                                unsigned char* base, F&& consume) {
-    constexpr int D = 2, UNR = kMfUnr;
-    auto slot = [&](int d, int u, int k) { return base + static_cast<size_t>((d * UNR + u) * VPL + k) * (kMfT * 16); };
-    const int n_it = (deg + UNR - 1) / UNR;
-    I i0 = 0, i1 = 0;
-    int cb = 0;
-    if (lane < deg) i0 = ldg_idx(col + begin + lane);
-    if (32 + lane < deg) i1 = ldg_idx(col + begin + 32 + lane);
-    auto issue = [&](int t) {
-        const int d = t & (D - 1);
-        const I ireg = ((t * UNR) >> 5) == cb ? i0 : i1;   // UNR divides 32: a stage never straddles two index batches
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int e = t * UNR + u;
-            const size_t off = static_cast<size_t>(__shfl_sync(0xffffffffu, ireg, e & 31)) * row_bytes;
-            if (e < deg) {
-#pragma unroll
-                for (int k = 0; k < VPL; ++k)
-                    if (valid[k]) cp_async16(slot(d, u, k), xb + off + static_cast<size_t>(lane + k * 32) * 16);
-            }
-        }
-        cp_async_commit();
-    };
-    if (n_it > 0) issue(0);
-    for (int t = 0; t < n_it; ++t) {
-        if (t + 1 < n_it) {
-            issue(t + 1);
-            if ((((t + 1) * UNR) >> 5) > cb) {
-                i0 = i1;
-                ++cb;
-                i1 = 0;
-                if ((cb + 1) * 32 + lane < deg) i1 = ldg_idx(col + begin + (cb + 1) * 32 + lane);
-            }
-        } else {
-            cp_async_commit();
-        }
-        cp_async_wait<1>();
-        const int d = t & (D - 1);
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int e = t * UNR + u;
-            if (e < deg) {
-#pragma unroll
-                for (int k = 0; k < VPL; ++k)
-                    if (valid[k]) consume(e, k, *reinterpret_cast<const Vec16*>(slot(d, u, k)));
-            }
-        }
-    }
-    cp_async_wait<0>();
-}
-
-template <typename I, int VPL, int MODE>
-__global__ void __launch_bounds__(kMfT)
-multi_aggr_staged_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const float* __restrict__ x,
-                         MultiOut outs, int64_t n_rows, int n_vec, LongRowPlan plan) {
-    extern __shared__ __align__(16) unsigned char mf_stage[];
-    const int lane = threadIdx.x & 31;
-    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    int64_t row, begin, end;
-    bool is_chunk;
-    if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;
-    const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
-    const int64_t feat = static_cast<int64_t>(n_vec) * 4;
-    const char* xb = reinterpret_cast<const char*>(x);
-    unsigned char* base = mf_stage + static_cast<size_t>(threadIdx.x) * 16;
-    const int deg = static_cast<int>(end - begin);
-    bool valid[VPL];
-    MultiState a[VPL][4];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-        valid[k] = lane + k * 32 < n_vec;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ms_init(a[k][i]);
-    }
-    staged_row_walk<I, VPL>(col, begin, deg, xb, row_bytes, valid, lane, base, [&](int, int k, const Vec16& v) {
-        float f[4];
-        ElemTraits<float>::unpack(v, f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ms_push<MODE>(a[k][i], f[i]);
-    });
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-        if (!valid[k]) continue;
-        const int v = lane + k * 32;
-        if (is_chunk) {
-            float* pb = plan.partials + static_cast<size_t>(item) * 6 * feat + static_cast<size_t>(v) * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                pb[i] = a[k][i].s;
-                pb[feat + i] = a[k][i].q;
-                pb[2 * feat + i] = a[k][i].mn;
-                pb[3 * feat + i] = a[k][i].mx;
-                pb[4 * feat + i] = a[k][i].cmn;
-                pb[5 * feat + i] = a[k][i].cmx;
-            }
-        } else {
-            ms_store_vec<float>(outs, static_cast<size_t>(row), row_bytes, static_cast<size_t>(v) * 16, a[k], end - begin);
-        }
-    }
-    if constexpr ((MODE & MA_NEED_TIES) != 0) {
-        // second walk while the row's sources are still in L2: the hit bits for the backward (see MultiOut::hit_mask)
-        if (outs.hit_mask && !is_chunk) {
-            uint8_t* mrow = outs.hit_mask + static_cast<size_t>(begin) * n_vec + lane;
-            staged_row_walk<I, VPL>(col, begin, deg, xb, row_bytes, valid, lane, base, [&](int e, int k, const Vec16& v) {
-                float f[4];
-                ElemTraits<float>::unpack(v, f);
-                unsigned bits = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) bits |= (f[i] == a[k][i].mn ? 1u << i : 0u) | (f[i] == a[k][i].mx ? 16u << i : 0u);
-                mrow[static_cast<size_t>(e) * n_vec + k * 32] = static_cast<uint8_t>(bits);
-            });
-        }
-    }
-}
-
 template <typename T, typename I, bool GATHER, int MODE>
 void multi_launch_mode(const I* rowptr, const I* col, const T* x, const MultiOut& outs, int64_t n_rows, int n_vec,
                        const LongRowPlan& plan, cudaStream_t stream) {
     const int64_t items = plan.n_chunks + n_rows;
-    if constexpr (GATHER && sizeof(T) == 4) {
-        if (get_option_attn_staged() && n_vec > 16 && n_vec <= 64) {
-            const unsigned blocks = static_cast<unsigned>(ceil_div(items, kMfT / 32));
-            const float* xf = reinterpret_cast<const float*>(x);
-            if (n_vec > 32)
-                multi_aggr_staged_kernel<I, 2, MODE><<<blocks, kMfT, 2 * kMfUnr * 2 * kMfT * 16, stream>>>(rowptr, col, xf, outs, n_rows, n_vec, plan);
-            else
-                multi_aggr_staged_kernel<I, 1, MODE><<<blocks, kMfT, 2 * kMfUnr * 1 * kMfT * 16, stream>>>(rowptr, col, xf, outs, n_rows, n_vec, plan);
-            return;
-        }
-    }
 #define B200MP_MA(G_)                                                                                            \
     multi_aggr_kernel<T, I, G_, GATHER, MODE><<<static_cast<unsigned>(ceil_div(items, 128 / G_)), 128, 0, stream>>>( \
         rowptr, col, x, outs, n_rows, n_vec, plan)
@@ -935,7 +849,23 @@ int multi_launch(const I* rowptr, const I* col, const T* x, MultiOut outs, int64
         const bool ties = outs.p[MA_TIES_MIN] || outs.p[MA_TIES_MAX];
         const bool mm = ties || outs.p[MA_MIN] || outs.p[MA_MAX];
         const bool sums = outs.p[MA_SUM] || outs.p[MA_MEAN] || outs.p[MA_VAR] || outs.p[MA_STD];
-        if (ties) multi_launch_mode<T, I, GATHER, kModeAllTies>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
+        bool done = false;
+        if constexpr (GATHER && sizeof(T) == 4) {
+            if (outs.hit_mask) {                                        // (the C entry point checked the shape)
+                if (get_option_multi_tune() == 5)
+                    multi_aggr_masked_kernel<I, 5><<<static_cast<unsigned>(ceil_div(n_rows, 4)), 128, 0, stream>>>(
+                        rowptr, col, reinterpret_cast<const float*>(x), outs, n_rows, n_vec, plan);
+                else
+                    multi_aggr_masked_kernel<I, 6><<<static_cast<unsigned>(ceil_div(n_rows, 4)), 128, 0, stream>>>(
+                        rowptr, col, reinterpret_cast<const float*>(x), outs, n_rows, n_vec, plan);
+                if (plan.n_chunks > 0)                                  // n_rows = 0: the chunk items only
+                    multi_aggr_kernel<T, I, 32, GATHER, kModeAllTies><<<static_cast<unsigned>(ceil_div(plan.n_chunks, 4)), 128, 0, stream>>>(
+                        rowptr, col, x, outs, 0, n_vec, plan);
+                done = true;
+            }
+        }
+        if (done) {
+        } else if (ties) multi_launch_mode<T, I, GATHER, kModeAllTies>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
         else if (mm && sums) multi_launch_mode<T, I, GATHER, kModeAll>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
         else if (mm) multi_launch_mode<T, I, GATHER, kModeMM>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
         else multi_launch_mode<T, I, GATHER, kModeSums>(rowptr, col, x, outs, n_rows, n_vec, plan, stream);
@@ -1044,6 +974,10 @@ using namespace b200mp;
         return B200MP_ERR_UNSUPPORTED;                                                                          \
     } while (0)
 
+extern "C" int b200mp_multi_aggr_mask_supported(int64_t feat, int val_dtype, int segment_mode) {
+    return val_dtype == B200MP_F32 && !segment_mode && feat % 4 == 0 && feat > 64 && feat <= 256 && get_option_attn_staged();
+}
+
 extern "C" int b200mp_multi_aggr_csr(const void* rowptr, const void* col, const void* x, void* out_sum,
                                      void* out_mean, void* out_min, void* out_max, void* out_var, void* out_std,
                                      float* ties_min, float* ties_max, void* hit_mask, int64_t n_rows, int64_t n_src,
@@ -1056,16 +990,12 @@ extern "C" int b200mp_multi_aggr_csr(const void* rowptr, const void* col, const 
     B200MP_CHECK_ARG(n_long_rows >= 0 && n_chunks >= 0);
     B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && partials && chunk > 0));
     // the hit mask is a by-product of the tie-counting fp32 vector sweep in gather mode
-    B200MP_CHECK_ARG(!hit_mask || (col && val_dtype == B200MP_F32 && feat % 4 == 0 && (ties_min || ties_max) && aligned16(x)));
+    B200MP_CHECK_ARG(!hit_mask || (col && b200mp_multi_aggr_mask_supported(feat, val_dtype, 0) && (ties_min || ties_max)));
     MultiOut outs{{out_sum, out_mean, out_min, out_max, out_var, out_std, ties_min, ties_max}, count_self_zero != 0,
                   static_cast<uint8_t*>(hit_mask)};
     LongRowPlan plan{long_rows, chunk_ptr, n_long_rows, n_long_rows ? n_chunks : 0, chunk, partials,
                      nullptr, 0, 0, nullptr, 0};
     DISPATCH_T_I(multi_typed, rowptr, col, x, outs, n_rows, feat, plan, static_cast<cudaStream_t>(stream));
-}
-
-extern "C" int b200mp_multi_aggr_mask_supported(int64_t feat, int val_dtype, int segment_mode) {
-    return val_dtype == B200MP_F32 && !segment_mode && feat % 4 == 0 && feat > 64 && feat <= 256 && get_option_attn_staged();
 }
 
 extern "C" int b200mp_multi_aggr_backward(const void* ptr, const void* idx, const void* x, const float* term_a,
