@@ -250,14 +250,15 @@ multi_aggr_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const
 // shape; parking the vectors makes pass 2 a shared-memory walk.
 constexpr int kKeep = 16;
 template <typename I, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+__global__ void __launch_bounds__(32, 4 * MINB)      // ONE warp per CTA: a CTA of four rows lives as long as its longest row, and
 multi_aggr_masked_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const float* __restrict__ x,
                          MultiOut outs, int64_t n_rows, int n_vec, LongRowPlan plan) {
     constexpr int UNR = 4;
     constexpr int kSums = MA_NEED_SUM | MA_NEED_SQ | MA_NEED_MM;
-    __shared__ Vec16 keep[kKeep][128];
-    const int lane = threadIdx.x & 31;
-    const int64_t item = plan.n_chunks + ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);   // rows only
+    // on a power-law graph that left 11 of the 24 resident warps busy (ncu: 17 % achieved of 37.5 % theoretical occupancy)
+    __shared__ Vec16 keep[kKeep][32];
+    const int lane = threadIdx.x;
+    const int64_t item = plan.n_chunks + static_cast<int64_t>(blockIdx.x);   // rows only
     int64_t row, begin, end;
     bool is_chunk;
     if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;
@@ -376,35 +377,58 @@ multi_aggr_combine_kernel(const I* __restrict__ rowptr, MultiOut outs, int64_t f
     }
 }
 
-// Hit mask of the hub rows' edges (their min / max are only known after the combine): one lane group per chunk.
-template <typename I, int G>
-__global__ void __launch_bounds__(128)
+// Hit bits and tie counts of the hub rows' edges (their min / max are only known after the combine): one warp per chunk,
+// four gathered vectors in flight.  The combine left ties = (0 | 1 for the zero self); the chunks add their counts
+// with atomics -- integers in fp32, exact in any order.
+template <typename I>
+__global__ void __launch_bounds__(32, 32)
 multi_aggr_mask_chunks_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const float* __restrict__ x,
                               const float* __restrict__ out_min, const float* __restrict__ out_max,
+                              float* __restrict__ ties_min, float* __restrict__ ties_max,
                               uint8_t* __restrict__ mask, int64_t n_rows, int n_vec, LongRowPlan plan) {
-    const int lig = threadIdx.x & (G - 1);
-    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    constexpr int UNR = 4;
+    const int lane = threadIdx.x;
+    const int64_t item = blockIdx.x;
     if (item >= plan.n_chunks) return;
     int64_t row, begin, end;
     bool is_chunk;
     if (!decode_item(item, rowptr, n_rows, plan, row, begin, end, is_chunk)) return;
     const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
-    for (int v = lig; v < n_vec; v += G) {
+    const char* xb = reinterpret_cast<const char*>(x);
+    for (int v = lane; v < n_vec; v += 32) {
         const size_t voff = static_cast<size_t>(v) * 16;
-        float mn[4], mx[4];
+        float mn[4], mx[4], cmn[4] = {0.f, 0.f, 0.f, 0.f}, cmx[4] = {0.f, 0.f, 0.f, 0.f};
         Vec16 t = {};
         if (out_min) t = ldg_row16(reinterpret_cast<const char*>(out_min) + static_cast<size_t>(row) * row_bytes + voff);
         ElemTraits<float>::unpack(t, mn);
         if (out_max) t = ldg_row16(reinterpret_cast<const char*>(out_max) + static_cast<size_t>(row) * row_bytes + voff);
         ElemTraits<float>::unpack(t, mx);
-        for (int64_t e = begin; e < end; ++e) {
-            float f[4];
-            ElemTraits<float>::unpack(ldg_row16(reinterpret_cast<const char*>(x) + static_cast<size_t>(ldg_idx(col + e)) * row_bytes + voff), f);
-            unsigned bits = 0;
+        for (int64_t e = begin; e < end; e += UNR) {
+            Vec16 buf[UNR];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                bits |= ((out_min && f[i] == mn[i]) ? 1u << i : 0u) | ((out_max && f[i] == mx[i]) ? 16u << i : 0u);
-            mask[static_cast<size_t>(e) * n_vec + v] = static_cast<uint8_t>(bits);
+            for (int u = 0; u < UNR; ++u)
+                if (e + u < end) buf[u] = ldg_row16(xb + static_cast<size_t>(ldg_idx(col + e + u)) * row_bytes + voff);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (e + u >= end) continue;
+                float f[4];
+                ElemTraits<float>::unpack(buf[u], f);
+                unsigned bits = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool hmn = out_min && f[i] == mn[i], hmx = out_max && f[i] == mx[i];
+                    cmn[i] += hmn ? 1.f : 0.f;
+                    cmx[i] += hmx ? 1.f : 0.f;
+                    bits |= (hmn ? 1u << i : 0u) | (hmx ? 16u << i : 0u);
+                }
+                mask[static_cast<size_t>(e + u) * n_vec + v] = static_cast<uint8_t>(bits);
+            }
+        }
+        const size_t o = static_cast<size_t>(row) * n_vec * 4 + static_cast<size_t>(v) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (ties_min && cmn[i] != 0.f) atomicAdd(ties_min + o + i, cmn[i]);
+            if (ties_max && cmx[i] != 0.f) atomicAdd(ties_max + o + i, cmx[i]);
         }
     }
 }
@@ -644,9 +668,8 @@ multi_aggr_backward_vec_kernel(const I* __restrict__ ptr, const I* __restrict__ 
 // MASK: the forward's hit bits (one byte per edge and vector, CSR edge order, addressed through t2csr) replace the two
 // 16-byte min / max vectors of the destination: 2 rows + 1 byte per edge instead of 4 rows, plus the tie-gradient
 // vectors of the lanes that hit (on a degree-d destination every edge attains the extremum of ~1/d of the features).
-constexpr int kMbT = 128;
-template <typename I, int VPL, bool MASK>
-__global__ void __launch_bounds__(kMbT)
+template <typename I, int VPL, bool MASK, int kMbT>
+__global__ void __launch_bounds__(kMbT, kMbT == 32 ? 20 : 5)
 multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict__ idx, const float* __restrict__ x,
                                   MultiGrad g, float* __restrict__ grad_x, int64_t n_items, int n_vec) {
     constexpr int D = 2, UNR = 2, NR = MASK ? 2 : 4;
@@ -804,18 +827,18 @@ multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict
                          ElemTraits<float>::pack(acc[k]));
 }
 
-template <typename I, int VPL, bool MASK>
+template <typename I, int VPL, bool MASK, int kMbT>
 int multi_bwd_staged_launch(const I* ptr, const I* idx, const float* x, const MultiGrad& g, float* grad_x, int64_t n_items,
                             int n_vec, cudaStream_t stream) {
     // 2 stages x 2 destinations x (2 | 4) rows x VPL vectors of 16 bytes per thread
     const size_t smem = static_cast<size_t>(2) * 2 * (MASK ? 2 : 4) * VPL * kMbT * 16;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-        B200MP_CUDA(cudaFuncSetAttribute(multi_aggr_backward_staged_kernel<I, VPL, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B200MP_CUDA(cudaFuncSetAttribute(multi_aggr_backward_staged_kernel<I, VPL, MASK, kMbT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
         attr_set = true;
     }
-    multi_aggr_backward_staged_kernel<I, VPL, MASK><<<static_cast<unsigned>(ceil_div(n_items, kMbT / 32)), kMbT, smem, stream>>>(
+    multi_aggr_backward_staged_kernel<I, VPL, MASK, kMbT><<<static_cast<unsigned>(ceil_div(n_items, kMbT / 32)), kMbT, smem, stream>>>(
         ptr, idx, x, g, grad_x, n_items, n_vec);
     B200MP_LAUNCH_CHECK();
     return B200MP_OK;
@@ -833,7 +856,9 @@ void multi_launch_mode(const I* rowptr, const I* col, const T* x, const MultiOut
     else if (n_vec <= 4) B200MP_MA(4);
     else if (n_vec <= 8) B200MP_MA(8);
     else if (n_vec <= 16) B200MP_MA(16);
-    else B200MP_MA(32);
+    else if (get_option_multi_tune() == 5) B200MP_MA(32);
+    else                                       // a warp per row: one-warp CTAs, so a long row does not hold three idle warps' slots
+        multi_aggr_kernel<T, I, 32, GATHER, MODE><<<static_cast<unsigned>(items), 32, 0, stream>>>(rowptr, col, x, outs, n_rows, n_vec, plan);
 #undef B200MP_MA
 }
 
@@ -853,14 +878,14 @@ int multi_launch(const I* rowptr, const I* col, const T* x, MultiOut outs, int64
         if constexpr (GATHER && sizeof(T) == 4) {
             if (outs.hit_mask) {                                        // (the C entry point checked the shape)
                 if (get_option_multi_tune() == 5)
-                    multi_aggr_masked_kernel<I, 5><<<static_cast<unsigned>(ceil_div(n_rows, 4)), 128, 0, stream>>>(
+                    multi_aggr_masked_kernel<I, 5><<<static_cast<unsigned>(n_rows), 32, 0, stream>>>(
                         rowptr, col, reinterpret_cast<const float*>(x), outs, n_rows, n_vec, plan);
                 else
-                    multi_aggr_masked_kernel<I, 6><<<static_cast<unsigned>(ceil_div(n_rows, 4)), 128, 0, stream>>>(
+                    multi_aggr_masked_kernel<I, 6><<<static_cast<unsigned>(n_rows), 32, 0, stream>>>(
                         rowptr, col, reinterpret_cast<const float*>(x), outs, n_rows, n_vec, plan);
-                if (plan.n_chunks > 0)                                  // n_rows = 0: the chunk items only
-                    multi_aggr_kernel<T, I, 32, GATHER, kModeAllTies><<<static_cast<unsigned>(ceil_div(plan.n_chunks, 4)), 128, 0, stream>>>(
-                        rowptr, col, x, outs, 0, n_vec, plan);
+                if (plan.n_chunks > 0)                                  // n_rows = 0: the chunk items only; no tie counters
+                    multi_aggr_kernel<T, I, 32, GATHER, kModeAll><<<static_cast<unsigned>(plan.n_chunks), 32, 0, stream>>>(
+                        rowptr, col, x, outs, 0, n_vec, plan);          // (multi_aggr_mask_chunks_kernel counts the hub rows' ties)
                 done = true;
             }
         }
@@ -882,9 +907,10 @@ int multi_launch(const I* rowptr, const I* col, const T* x, MultiOut outs, int64
         if constexpr (GATHER && sizeof(T) == 4) {
             if (outs.hit_mask) {
                 const int n_vec = static_cast<int>(row_bytes / 16);
-                multi_aggr_mask_chunks_kernel<I, 32><<<static_cast<unsigned>(ceil_div(plan.n_chunks, 128 / 32)), 128, 0, stream>>>(
+                multi_aggr_mask_chunks_kernel<I><<<static_cast<unsigned>(plan.n_chunks), 32, 0, stream>>>(
                     rowptr, col, reinterpret_cast<const float*>(x), static_cast<const float*>(outs.p[MA_MIN]),
-                    static_cast<const float*>(outs.p[MA_MAX]), outs.hit_mask, n_rows, n_vec, plan);
+                    static_cast<const float*>(outs.p[MA_MAX]), static_cast<float*>(outs.p[MA_TIES_MIN]),
+                    static_cast<float*>(outs.p[MA_TIES_MAX]), outs.hit_mask, n_rows, n_vec, plan);
                 B200MP_LAUNCH_CHECK();
             }
         }
@@ -934,11 +960,12 @@ int multi_bwd_typed(const void* ptr, const void* idx, const void* x, MultiGrad g
             const I* ix = static_cast<const I*>(idx);
             const float* xf = static_cast<const float*>(x);
             float* gx = static_cast<float*>(grad_x);
-            const bool masked = g.hit_mask != nullptr;
-            if (n_vec > 32) return masked ? multi_bwd_staged_launch<I, 2, true>(p, ix, xf, g, gx, n_items, n_vec, stream)
-                                          : multi_bwd_staged_launch<I, 2, false>(p, ix, xf, g, gx, n_items, n_vec, stream);
-            return masked ? multi_bwd_staged_launch<I, 1, true>(p, ix, xf, g, gx, n_items, n_vec, stream)
-                          : multi_bwd_staged_launch<I, 1, false>(p, ix, xf, g, gx, n_items, n_vec, stream);
+            // one-warp CTAs (multi_tune 6, default): no warp waits for the longest of four rows
+            if (get_option_multi_tune() == 5)
+                return n_vec > 32 ? multi_bwd_staged_launch<I, 2, true, 128>(p, ix, xf, g, gx, n_items, n_vec, stream)
+                                  : multi_bwd_staged_launch<I, 1, true, 128>(p, ix, xf, g, gx, n_items, n_vec, stream);
+            return n_vec > 32 ? multi_bwd_staged_launch<I, 2, true, 32>(p, ix, xf, g, gx, n_items, n_vec, stream)
+                              : multi_bwd_staged_launch<I, 1, true, 32>(p, ix, xf, g, gx, n_items, n_vec, stream);
         } else
             multi_bwd_vec_launch<I, false>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
                                            static_cast<const float*>(x), g, static_cast<float*>(grad_x), n_items, n_vec, stream);
