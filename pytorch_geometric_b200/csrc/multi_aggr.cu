@@ -67,8 +67,9 @@ __device__ __forceinline__ void ms_push(MultiState& a, float v) {
         if (v < a.mn || v != v) { a.mn = v; a.cmn = 1.f; } else if (v == a.mn) a.cmn += 1.f;
         if (v > a.mx || v != v) { a.mx = v; a.cmx = 1.f; } else if (v == a.mx) a.cmx += 1.f;
     } else if (MODE & MA_NEED_MM) {
-        a.mn = (v < a.mn || v != v) ? v : a.mn;
-        a.mx = (v > a.mx || v != v) ? v : a.mx;
+        // NaN-propagating min / max (= "v < mn || v != v ? v : mn", ATen's amin / amax rule) in one instruction each
+        asm("min.NaN.f32 %0, %1, %2;" : "=f"(a.mn) : "f"(a.mn), "f"(v));
+        asm("max.NaN.f32 %0, %1, %2;" : "=f"(a.mx) : "f"(a.mx), "f"(v));
     }
 }
 __device__ __forceinline__ void ms_merge(MultiState& a, const MultiState& b) {   // a then b, in edge order
@@ -877,12 +878,8 @@ int multi_launch(const I* rowptr, const I* col, const T* x, MultiOut outs, int64
         bool done = false;
         if constexpr (GATHER && sizeof(T) == 4) {
             if (outs.hit_mask) {                                        // (the C entry point checked the shape)
-                if (get_option_multi_tune() == 5)
-                    multi_aggr_masked_kernel<I, 5><<<static_cast<unsigned>(n_rows), 32, 0, stream>>>(
-                        rowptr, col, reinterpret_cast<const float*>(x), outs, n_rows, n_vec, plan);
-                else
-                    multi_aggr_masked_kernel<I, 6><<<static_cast<unsigned>(n_rows), 32, 0, stream>>>(
-                        rowptr, col, reinterpret_cast<const float*>(x), outs, n_rows, n_vec, plan);
+                multi_aggr_masked_kernel<I, 5><<<static_cast<unsigned>(n_rows), 32, 0, stream>>>(
+                    rowptr, col, reinterpret_cast<const float*>(x), outs, n_rows, n_vec, plan);   // (<I, 6>: 80 registers with spills, 63.0 vs 60.5 ms)
                 if (plan.n_chunks > 0)                                  // n_rows = 0: the chunk items only; no tie counters
                     multi_aggr_kernel<T, I, 32, GATHER, kModeAll><<<static_cast<unsigned>(plan.n_chunks), 32, 0, stream>>>(
                         rowptr, col, x, outs, 0, n_vec, plan);          // (multi_aggr_mask_chunks_kernel counts the hub rows' ties)
