@@ -82,8 +82,10 @@ __device__ __forceinline__ void merge_ms(float m1, float m2, float& M, float& c1
 // STAGED (VPL == 1, G >= 8): the row vectors (and GAT's a_src scalars) of iteration t + 1 are in flight as cp.async
 // copies into lane-private shared-memory slots while iteration t is computed -- twice the rows in flight per warp at the
 // same register budget (the sweeps are latency-bound: 58 % long-scoreboard stalls in profiles/r2_attn_v2.summary.csv).
-template <typename T, typename I, int G, int VPL, int MODE, bool STAGED = false>
-__global__ void __launch_bounds__(kAttnT, VPL == 1 ? 8 : 5)       // <= 64 registers: 32 warps / SM (latency-bound gather)
+// BT = threads per CTA.  32 (one warp = one work item per CTA) for the staged kernels: a 4-warp CTA holds its slots until
+// the longest of its four power-law rows is done (ncu, r2_attn_v3: 35 % achieved of 50 % theoretical occupancy).
+template <typename T, typename I, int G, int VPL, int MODE, bool STAGED = false, int BT = kAttnT>
+__global__ void __launch_bounds__(BT, (VPL == 1 ? 8 : 5) * (kAttnT / BT))       // <= 64 registers: 32 warps / SM
 attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArgs a, T* __restrict__ out,
                 float* __restrict__ row_max, float* __restrict__ row_den, int64_t n_rows, LongRowPlan plan,
                 float* __restrict__ part_ms) {
@@ -127,9 +129,9 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
         constexpr int NV = MODE == ATTN_DOT ? 2 : 1;                // value (+ key) vector per edge
         constexpr int PER = S * UNR;                                // edges per iteration of the warp
         unsigned char* vslots = attn_stage + static_cast<size_t>(threadIdx.x) * 16;
-        float* sslots = reinterpret_cast<float*>(attn_stage + static_cast<size_t>(D) * UNR * NV * kAttnT * 16) + threadIdx.x;
-        auto vslot = [&](int d, int u, int v) { return vslots + static_cast<size_t>((d * UNR + u) * NV + v) * (kAttnT * 16); };
-        auto sslot = [&](int d, int u) { return sslots + (d * UNR + u) * kAttnT; };
+        float* sslots = reinterpret_cast<float*>(attn_stage + static_cast<size_t>(D) * UNR * NV * BT * 16) + threadIdx.x;
+        auto vslot = [&](int d, int u, int v) { return vslots + static_cast<size_t>((d * UNR + u) * NV + v) * (BT * 16); };
+        auto sslot = [&](int d, int u) { return sslots + (d * UNR + u) * BT; };
         const int deg = static_cast<int>(end - begin);
         const int n_it = (deg + PER - 1) / PER;
         const size_t off = static_cast<size_t>(lig) * 16;
@@ -690,8 +692,8 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
 }
 
 // ------------------------------------------------------------------------------------------------ backward, source sweep
-template <typename T, typename I, int G, int VPL, int MODE, bool STAGED = false>
-__global__ void __launch_bounds__(kAttnT)      // no register cap: capping at 64 serialised the row loads (8.0 -> 14.8 ms)
+template <typename T, typename I, int G, int VPL, int MODE, bool STAGED = false, int BT = kAttnT>
+__global__ void __launch_bounds__(BT)          // no register cap: capping at 64 serialised the row loads (8.0 -> 14.8 ms)
 attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t, const I* __restrict__ t2csr, AttnArgs a,
                     const T* __restrict__ grad_out, const float* __restrict__ pair, T* __restrict__ grad_v,
                     T* __restrict__ grad_k, float* __restrict__ grad_s_src, int64_t n_src, LongRowPlan plan) {
@@ -754,9 +756,9 @@ attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t,
         extern __shared__ __align__(16) unsigned char attn_stage[];
         constexpr int D = 2, NV = MODE == ATTN_GAT ? 1 : 2, PER = S * UNR;
         unsigned char* vslots = attn_stage + static_cast<size_t>(threadIdx.x) * 16;
-        float2* pslots = reinterpret_cast<float2*>(attn_stage + static_cast<size_t>(D) * UNR * NV * kAttnT * 16) + threadIdx.x;
-        auto vslot = [&](int d, int u, int v) { return vslots + static_cast<size_t>((d * UNR + u) * NV + v) * (kAttnT * 16); };
-        auto pslot = [&](int d, int u) { return pslots + (d * UNR + u) * kAttnT; };
+        float2* pslots = reinterpret_cast<float2*>(attn_stage + static_cast<size_t>(D) * UNR * NV * BT * 16) + threadIdx.x;
+        auto vslot = [&](int d, int u, int v) { return vslots + static_cast<size_t>((d * UNR + u) * NV + v) * (BT * 16); };
+        auto pslot = [&](int d, int u) { return pslots + (d * UNR + u) * BT; };
         const int deg = static_cast<int>(end - begin);
         const int n_it = (deg + PER - 1) / PER;
         const size_t off = static_cast<size_t>(lig) * 16;
@@ -978,15 +980,21 @@ int attn_forward_typed(const void* rowptr_, const void* col_, AttnArgs a, void* 
     const unsigned blocks = static_cast<unsigned>(ceil_div(items, kAttnT / 32));
 #define ATTN_FWD(G_, V_) attn_fwd_kernel<T, I, G_, V_, MODE><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, out, row_max, row_den, n_rows, plan, part_ms)
 #define ATTN_FWD_STAGED(G_) attn_fwd_kernel<T, I, G_, 1, MODE, true><<<blocks, kAttnT, stage_bytes, s>>>(rowptr, col, a, out, row_max, row_den, n_rows, plan, part_ms)
+#define ATTN_FWD_STAGED1(G_) attn_fwd_kernel<T, I, G_, 1, MODE, true, 32><<<static_cast<unsigned>(items), 32, stage_bytes / (kAttnT / 32), s>>>(rowptr, col, a, out, row_max, row_den, n_rows, plan, part_ms)
     // lane-private cp.async slots: 2 iterations x 4 edges x (value (+ key) vector + a_src scalar) per thread
     const size_t stage_bytes = static_cast<size_t>(2) * 4 * kAttnT * ((MODE == ATTN_DOT ? 2 : 1) * 16 + 4);
-    if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
+    if (get_option_attn_staged() == 2 && n_vec > 4 && n_vec <= 32) {          // one-warp CTAs
+        if (n_vec <= 8) ATTN_FWD_STAGED1(8);
+        else if (n_vec <= 16) ATTN_FWD_STAGED1(16);
+        else ATTN_FWD_STAGED1(32);
+    } else if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
         if (n_vec <= 8) ATTN_FWD_STAGED(8);
         else if (n_vec <= 16) ATTN_FWD_STAGED(16);
         else ATTN_FWD_STAGED(32);
     } else {
         ATTN_BY_SHAPE(ATTN_FWD);
     }
+#undef ATTN_FWD_STAGED1
 #undef ATTN_FWD_STAGED
 #undef ATTN_FWD
     B200MP_LAUNCH_CHECK();
@@ -1053,14 +1061,20 @@ int attn_backward_typed(const void* rowptr_, const void* col_, const void* rowpt
         const unsigned blocks = static_cast<unsigned>(ceil_div(items, kAttnT / 32));
 #define ATTN_SRC(G_, V_) attn_bwd_src_kernel<T, I, G_, V_, MODE><<<blocks, kAttnT, 0, s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
 #define ATTN_SRC_STAGED(G_) attn_bwd_src_kernel<T, I, G_, 1, MODE, true><<<blocks, kAttnT, src_stage, s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
+#define ATTN_SRC_STAGED1(G_) attn_bwd_src_kernel<T, I, G_, 1, MODE, true, 32><<<static_cast<unsigned>(items), 32, src_stage / (kAttnT / 32), s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
         const size_t src_stage = static_cast<size_t>(2) * 4 * kAttnT * ((MODE == ATTN_GAT ? 1 : 2) * 16 + 8);
-        if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
+        if (get_option_attn_staged() == 2 && n_vec > 4 && n_vec <= 32) {
+            if (n_vec <= 8) ATTN_SRC_STAGED1(8);
+            else if (n_vec <= 16) ATTN_SRC_STAGED1(16);
+            else ATTN_SRC_STAGED1(32);
+        } else if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
             if (n_vec <= 8) ATTN_SRC_STAGED(8);
             else if (n_vec <= 16) ATTN_SRC_STAGED(16);
             else ATTN_SRC_STAGED(32);
         } else {
             ATTN_BY_SHAPE(ATTN_SRC);
         }
+#undef ATTN_SRC_STAGED1
 #undef ATTN_SRC_STAGED
 #undef ATTN_SRC
         B200MP_LAUNCH_CHECK();

@@ -104,7 +104,7 @@ extern "C" int b200mp_set_option(const char* name, int value) {
         return B200MP_OK;
     }
     if (strcmp(name, "attn_staged") == 0) {
-        if (value != 0 && value != 1) return B200MP_ERR_INVALID_ARG;
+        if (value < 0 || value > 2) return B200MP_ERR_INVALID_ARG;      // 2: staged + one-warp CTAs (forward, source sweep)
         b200mp::g_attn_staged = value;
         return B200MP_OK;
     }

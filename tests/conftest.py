@@ -15,6 +15,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _engine_options_from_env():
+    """B200MP_ATTN_STAGED / B200MP_MULTI_TUNE select a kernel variant for the whole session (GPU box only), so the same
+    parity tests can be run against every variant that benchmarks compare."""
+    import torch
+    if torch.cuda.is_available():
+        from pytorch_geometric_b200 import ops
+        for env, opt in (("B200MP_ATTN_STAGED", "attn_staged"), ("B200MP_MULTI_TUNE", "multi_tune")):
+            if os.environ.get(env) is not None:
+                ops.set_option(opt, int(os.environ[env]))
+    yield
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
         return {k: z[k] for k in z.files}
