@@ -277,6 +277,23 @@ int b200mp_multi_aggr_backward(const void* ptr, const void* idx, const void* x, 
                                void* grad_x, int64_t n_items, int64_t feat, int segment_mode, int idx_dtype,
                                int val_dtype, void* stream);
 
+/* ------------------------------------------------------------------ node-level attention terms
+ * s_a[n,h] = sum_c x[n,h,c] * att_a[h,c] (and s_b with att_b from the same read of x; att_b / s_b nullable together):
+ * GATConv's alpha_src / alpha_dst = (x * att).sum(-1) (nn/conv/gat_conv.py:330-331) without the [N,H,C] product tensor.
+ * x: [n_rows, heads*chan] of val_dtype (fp32 / bf16), att_*: fp32 [heads*chan], s_*: fp32 [n_rows, heads].
+ * Supported when chan * sizeof(val) is a multiple of 16 and a power-of-two number (<= 32) of 16-byte vectors, and a row has
+ * at most 256 vectors (b200mp_head_dot_supported); other shapes are the caller's business.
+ * Backward in one pass: grad_x = g_a (x) att_a + g_b (x) att_b (+ add, nullable: e.g. the attention's own grad_v), and
+ * per-CTA partial rows part_* [n_parts, heads*chan] fp32 of grad_att_* = sum_n g_*[n,h] * x[n,h,c] (fold them with
+ * b200mp_column_sum; n_parts from b200mp_head_dot_parts).  grad_x nullable (x does not need a gradient). */
+int b200mp_head_dot_supported(int64_t heads, int64_t chan, int val_dtype);
+int64_t b200mp_head_dot_parts(int64_t n_rows, int64_t heads, int64_t chan, int val_dtype);
+int b200mp_head_dot(const void* x, const float* att_a, const float* att_b, float* s_a, float* s_b, int64_t n_rows,
+                    int64_t heads, int64_t chan, int val_dtype, void* stream);
+int b200mp_head_dot_backward(const void* x, const float* att_a, const float* att_b, const float* g_a, const float* g_b,
+                             const void* add, void* grad_x, float* part_a, float* part_b, int64_t n_parts,
+                             int64_t n_rows, int64_t heads, int64_t chan, int val_dtype, void* stream);
+
 /* ------------------------------------------------------------------ fused GAT attention + aggregation
  * One sweep over the destination-sorted CSR per (node, head):
  *   logit_e = leaky_relu(a_src[col[e],h] + a_dst[i,h], slope)

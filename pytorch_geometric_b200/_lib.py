@@ -71,6 +71,10 @@ _SIGS = {
     "b200mp_softmax_edge_op": (_INT, [_INT, _P, _P, _P, _P, _P, _I64, _I64, _INT, _P]),
     "b200mp_multi_aggr_csr": (_INT, [_P] * 12 + [_I64, _I64, _I64, _INT, _P, _P, _I64, _I64, _I64, _P, _INT, _INT, _P]),
     "b200mp_multi_aggr_mask_supported": (_INT, [_I64, _INT, _INT]),
+    "b200mp_head_dot_supported": (_INT, [_I64, _I64, _INT]),
+    "b200mp_head_dot_parts": (_I64, [_I64, _I64, _I64, _INT]),
+    "b200mp_head_dot": (_INT, [_P] * 5 + [_I64, _I64, _I64, _INT, _P]),
+    "b200mp_head_dot_backward": (_INT, [_P] * 9 + [_I64, _I64, _I64, _I64, _INT, _P]),
     "b200mp_multi_aggr_prepare_backward": (_INT, [_P] * 15 + [_I64, _I64, _INT, _INT, _INT, _P]),
     "b200mp_multi_aggr_backward": (_INT, [_P] * 12 + [_I64, _I64, _INT, _INT, _INT, _P]),
 }

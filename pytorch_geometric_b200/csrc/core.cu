@@ -54,7 +54,7 @@ static int g_gemm_mode = 1;   // TS mode (A operand in TMEM) measured 25 % faste
 int get_option_gemm_mode() { return g_gemm_mode; }
 static int g_spmm_tune = 0;
 int get_option_spmm_tune() { return g_spmm_tune; }
-static int g_attn_staged = 1;   // cp.async-staged attention forward (csrc/attention.cu); 0 = register-staged loop
+static int g_attn_staged = 2;   // cp.async-staged attention sweeps (csrc/attention.cu): 2 = with one-warp CTAs, 1 = 4-warp CTAs, 0 = register-staged loop
 int get_option_attn_staged() { return g_attn_staged; }
 static int g_multi_tune = 6;    // resident CTAs per SM the masked multi-aggregation sweep is compiled for (5 | 6), multi_aggr.cu
 int get_option_multi_tune() { return g_multi_tune; }

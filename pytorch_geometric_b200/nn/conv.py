@@ -189,9 +189,41 @@ def gin_aggregate(x_src: Tensor, x_dst: Optional[Tensor], graph: CSRGraph, eps) 
     return out
 
 
-def _head_dot(xh: Tensor, att: Tensor, H: int, C: int) -> Tensor:
-    """(xh.view(-1,H,C) * att).sum(-1) in fp32: the node-level attention terms (gat_conv.py:330-331)."""
-    return (xh.view(-1, H, C).float() * att.view(1, H, C).float()).sum(dim=-1)
+class _HeadDot(torch.autograd.Function):
+    """(s_a, s_b) = ((xh * att_a).sum(-1), (xh * att_b).sum(-1)) from ONE read of xh, and a one-pass backward
+    (csrc/head_dot.cu) instead of the ten broadcast-multiply / reduce launches autograd makes of gat_conv.py:330-331."""
+
+    @staticmethod
+    def forward(ctx, xh, att_a, att_b, H, C):
+        s_a, s_b = ops.head_dot(xh, att_a, att_b, H, C)
+        ctx.save_for_backward(xh, att_a, att_b)
+        ctx.hc = (H, C)
+        return s_a, s_b                                                   # s_b is None without att_b
+
+    @staticmethod
+    def backward(ctx, g_a, g_b):
+        xh, att_a, att_b = ctx.saved_tensors
+        H, C = ctx.hc
+        if g_a is None:
+            g_a = torch.zeros(xh.size(0), H, dtype=torch.float32, device=xh.device)
+        if att_b is not None and g_b is None:
+            g_b = torch.zeros(xh.size(0), H, dtype=torch.float32, device=xh.device)
+        gx, ga, gb = ops.head_dot_backward(xh, att_a, att_b, g_a, g_b if att_b is not None else None, None, H, C,
+                                           ctx.needs_input_grad[0])
+        ga = ga.view_as(att_a).to(att_a.dtype) if ctx.needs_input_grad[1] else None
+        gb = gb.view_as(att_b).to(att_b.dtype) if att_b is not None and ctx.needs_input_grad[2] else None
+        return gx, ga, gb, None, None
+
+
+def _head_dot(xh: Tensor, att: Tensor, H: int, C: int, att2: Optional[Tensor] = None):
+    """(xh.view(-1,H,C) * att).sum(-1) in fp32: the node-level attention terms (gat_conv.py:330-331).  With att2 the
+    pair of terms for two attention vectors over the same features."""
+    if ops.head_dot_supported(xh, H, C):
+        s_a, s_b = _HeadDot.apply(xh, att, att2, H, C)
+        return s_a if att2 is None else (s_a, s_b)
+    x3 = xh.view(-1, H, C).float()
+    s_a = (x3 * att.view(1, H, C).float()).sum(dim=-1)
+    return s_a if att2 is None else (s_a, (x3 * att2.view(1, H, C).float()).sum(dim=-1))
 
 
 def _finish_heads(out: Tensor, H: int, C: int, concat: bool, res: Optional[Tensor], bias: Optional[Tensor]) -> Tensor:
@@ -210,11 +242,14 @@ def gat_conv(xh_src: Tensor, xh_dst: Optional[Tensor], graph: CSRGraph, att_src:
     """GATConv after its linear maps (gat_conv.py:330-385): xh_* = lin(x) [n, H*C]; xh_dst None = the sources are the
     destinations; att_dst None = no destination term (x = (x_src, None)).  s_edge [E, H] =
     (lin_edge(edge_attr) * att_edge).sum(-1) aligned with the edges the graph was built from (edge_dim)."""
-    a_src = _head_dot(xh_src, att_src, H, C)
     if att_dst is None:
+        a_src = _head_dot(xh_src, att_src, H, C)
         a_dst = a_src.new_zeros(graph.num_dst, H)
+    elif xh_dst is None:
+        a_src, a_dst = _head_dot(xh_src, att_src, H, C, att_dst)         # both terms from one read of the features
     else:
-        a_dst = _head_dot(xh_src if xh_dst is None else xh_dst, att_dst, H, C)
+        a_src = _head_dot(xh_src, att_src, H, C)
+        a_dst = _head_dot(xh_dst, att_dst, H, C)
     r = Fn.attention("gat", graph, H, C, v=xh_src, s_src=a_src, s_dst=a_dst, s_edge=s_edge, negative_slope=negative_slope,
                      return_alpha=return_alpha)
     out, alpha = r if return_alpha else (r, None)

@@ -643,6 +643,49 @@ def column_sum(x: Tensor) -> Tensor:
     return out
 
 
+def head_dot_supported(x: Tensor, heads: int, chan: int) -> bool:
+    return (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.dim() == 2 and x.size(1) == heads * chan
+            and bool(lib().b200mp_head_dot_supported(heads, chan, _vdt(x))))
+
+
+def head_dot(x: Tensor, att_a: Tensor, att_b: Optional[Tensor], heads: int, chan: int):
+    """(s_a, s_b) with s_*[n, h] = sum_c x[n, h, c] * att_*[h, c] in fp32, one read of x (b200mp_head_dot)."""
+    _cuda(x, att_a, att_b)
+    x = x.contiguous()
+    att_a = att_a.reshape(-1).float().contiguous()
+    att_b = None if att_b is None else att_b.reshape(-1).float().contiguous()
+    n = x.size(0)
+    s_a = torch.empty(n, heads, dtype=torch.float32, device=x.device)
+    s_b = None if att_b is None else torch.empty(n, heads, dtype=torch.float32, device=x.device)
+    _timed("head_dot", 1, lib().b200mp_head_dot, _p(x), _p(att_a), _p(att_b), _p(s_a), _p(s_b), n, heads, chan, _vdt(x),
+           _stream())
+    return s_a, s_b
+
+
+def head_dot_backward(x: Tensor, att_a: Tensor, att_b: Optional[Tensor], g_a: Tensor, g_b: Optional[Tensor],
+                      add: Optional[Tensor], heads: int, chan: int, want_grad_x: bool = True):
+    """(grad_x, grad_att_a, grad_att_b): grad_x = g_a (x) att_a + g_b (x) att_b (+ add), grad_att_* fp32 [heads*chan]."""
+    _cuda(x, att_a, att_b, g_a, g_b, add)
+    x = x.contiguous()
+    att_a = att_a.reshape(-1).float().contiguous()
+    att_b = None if att_b is None else att_b.reshape(-1).float().contiguous()
+    g_a = g_a.float().contiguous()
+    g_b = None if g_b is None else g_b.float().contiguous()
+    if add is not None:
+        add = add.to(x.dtype).contiguous()
+    n, F = x.shape
+    gx = torch.empty_like(x) if want_grad_x else None
+    parts = int(lib().b200mp_head_dot_parts(n, heads, chan, _vdt(x)))
+    if parts == 0:
+        z = torch.zeros(F, dtype=torch.float32, device=x.device)
+        return gx, z, (None if att_b is None else z.clone())
+    pa = torch.empty(parts, F, dtype=torch.float32, device=x.device)
+    pb = None if att_b is None else torch.empty(parts, F, dtype=torch.float32, device=x.device)
+    _timed("head_dot_backward", 1, lib().b200mp_head_dot_backward, _p(x), _p(att_a), _p(att_b), _p(g_a), _p(g_b), _p(add),
+           _p(gx), _p(pa), _p(pb), parts, n, heads, chan, _vdt(x), _stream())
+    return gx, column_sum(pa), (None if pb is None else column_sum(pb))
+
+
 MULTI_AGGRS = ("sum", "mean", "min", "max", "var", "std")
 MULTI_HIT_MASK = True       # emit the forward's hit bits for the backward (A/B switch for benchmarks)
 

@@ -159,3 +159,43 @@ def test_gatv2_attention_vs_oracle_and_golden_layer():
         np.testing.assert_allclose(xt.grad.cpu().numpy(), g[f"{tag}_gx"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(conv.att.grad.view(H, C).cpu().numpy(), g[f"{tag}_g_att"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(conv.lin_l.weight.grad.cpu().numpy(), g[f"{tag}_g_lin_l_w"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("H,C,dtype,pair", [(8, 16, torch.bfloat16, True), (8, 16, torch.float32, True),
+                                           (3, 4, torch.float32, True), (1, 128, torch.float32, False),
+                                           (2, 8, torch.bfloat16, True), (5, 32, torch.float32, False),
+                                           (4, 6, torch.float32, True)])
+def test_head_dot_terms_and_their_backward(H, C, dtype, pair):
+    """alpha_src / alpha_dst = (x * att).sum(-1) (gat_conv.py:330-331) from one read of x (csrc/head_dot.cu), and the
+    one-pass backward, against the formula in fp64; (4, 6) is a shape the kernel does not take (torch fallback)."""
+    from pytorch_geometric_b200 import ops
+    from pytorch_geometric_b200.nn.conv import _head_dot
+    g = torch.Generator(device=DEV).manual_seed(H * 100 + C)
+    N = 3001
+    x = torch.randn(N, H * C, device=DEV, generator=g).to(dtype).requires_grad_()
+    att_a = torch.randn(1, H, C, device=DEV, generator=g).requires_grad_()
+    att_b = torch.randn(1, H, C, device=DEV, generator=g).requires_grad_() if pair else None
+    assert ops.head_dot_supported(x, H, C) == ((C * x.element_size()) % 16 == 0)
+    r = _head_dot(x, att_a, H, C, att_b)
+    s_a, s_b = r if pair else (r, None)
+    x64 = x.detach().double().requires_grad_()
+    a64 = att_a.detach().double().requires_grad_()
+    b64 = att_b.detach().double().requires_grad_() if pair else None
+    ra = (x64.view(N, H, C) * a64).sum(-1)
+    rb = (x64.view(N, H, C) * b64).sum(-1) if pair else None
+    tol = 1e-5 * float((x64.view(N, H, C).abs() * a64.abs()).sum(-1).max())
+    assert float((s_a.double() - ra).abs().max()) <= tol
+    ga = torch.randn(N, H, device=DEV, generator=g)
+    gb = torch.randn(N, H, device=DEV, generator=g) if pair else None
+    if pair:
+        assert float((s_b.double() - rb).abs().max()) <= 1e-5 * float((x64.view(N, H, C).abs() * b64.abs()).sum(-1).max())
+        torch.autograd.backward([s_a, s_b], [ga, gb])
+        torch.autograd.backward([ra, rb], [ga.double(), gb.double()])
+    else:
+        s_a.backward(ga)
+        ra.backward(ga.double())
+    gx_tol = (2.0 ** -8 if dtype == torch.bfloat16 else 1e-5) * float(x64.grad.abs().max() + 1)
+    assert float((x.grad.double() - x64.grad).abs().max()) <= gx_tol
+    for got, ref in ((att_a.grad, a64.grad), ) + (((att_b.grad, b64.grad), ) if pair else ()):
+        assert got.shape == ref.shape
+        assert float((got.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max() + N ** 0.5)
