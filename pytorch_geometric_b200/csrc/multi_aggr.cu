@@ -940,6 +940,82 @@ void multi_bwd_vec_launch(const I* ptr, const I* idx, const float* x, const Mult
 #undef B200MP_MB
 }
 
+// Segment-mode backward (one destination per message, messages sorted by destination): a lane group walks kSegRun
+// CONSECUTIVE messages, two in flight.  The one-message-per-lane-group form launched E / 8 CTAs of 8 messages each
+// (12.5 M CTAs at the 100 M-message shape) and had one dependent load chain per thread; consecutive messages mostly share
+// their destination, so its four rows are read through L1 (ld.global.nc with allocation) instead of L2 every time.
+constexpr int kSegRun = 8;
+template <typename I, int G>
+__global__ void __launch_bounds__(128, 6)
+multi_aggr_backward_segment_kernel(const I* __restrict__ dst_of_msg, const float* __restrict__ x, MultiGrad g,
+                                   float* __restrict__ grad_x, int64_t n_msgs, int n_vec) {
+    constexpr int UNR = 2;
+    const int lig = threadIdx.x & (G - 1);
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    const int64_t begin = item * kSegRun;
+    if (begin >= n_msgs) return;
+    const int64_t end = begin + kSegRun < n_msgs ? begin + kSegRun : n_msgs;
+    const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
+    auto ld_l1 = [](const void* p) { return *reinterpret_cast<const Vec16*>(__builtin_assume_aligned(p, 16)); };
+    for (int v = lig; v < n_vec; v += G) {
+        const size_t voff = static_cast<size_t>(v) * 16;
+        for (int64_t e = begin; e < end; e += UNR) {
+            Vec16 xb[UNR], b[UNR][4];
+            size_t offs[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (e + u < end) {
+                    xb[u] = ldg_stream16(reinterpret_cast<const char*>(x) + static_cast<size_t>(e + u) * row_bytes + voff);
+                    const size_t off = static_cast<size_t>(dst_of_msg[e + u]) * row_bytes + voff;
+                    offs[u] = off;
+                    if (g.a) b[u][0] = ld_l1(reinterpret_cast<const char*>(g.a) + off);
+                    if (g.b) b[u][1] = ld_l1(reinterpret_cast<const char*>(g.b) + off);
+                    if (g.mn) b[u][2] = ld_l1(static_cast<const char*>(g.mn) + off);
+                    if (g.mx) b[u][3] = ld_l1(static_cast<const char*>(g.mx) + off);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (e + u >= end) continue;
+                float xv[4], t[4];
+                ElemTraits<float>::unpack(xb[u], xv);
+                bool hit_mn = false, hit_mx = false;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    hit_mn = hit_mn || (g.mn && xv[i] == __uint_as_float(b[u][2].w[i]));
+                    hit_mx = hit_mx || (g.mx && xv[i] == __uint_as_float(b[u][3].w[i]));
+                }
+                Vec16 gmn = {}, gmx = {};
+                if (hit_mn) gmn = ld_l1(reinterpret_cast<const char*>(g.gmin) + offs[u]);
+                if (hit_mx) gmx = ld_l1(reinterpret_cast<const char*>(g.gmax) + offs[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    t[i] = g.a ? __uint_as_float(b[u][0].w[i]) : 0.f;
+                    if (g.b) t[i] = fmaf(xv[i], __uint_as_float(b[u][1].w[i]), t[i]);
+                    if (hit_mn && xv[i] == __uint_as_float(b[u][2].w[i])) t[i] += __uint_as_float(gmn.w[i]);
+                    if (hit_mx && xv[i] == __uint_as_float(b[u][3].w[i])) t[i] += __uint_as_float(gmx.w[i]);
+                }
+                stg_stream16(reinterpret_cast<char*>(grad_x) + static_cast<size_t>(e + u) * row_bytes + voff, ElemTraits<float>::pack(t));
+            }
+        }
+    }
+}
+
+template <typename I>
+void multi_bwd_segment_launch(const I* idx, const float* x, const MultiGrad& g, float* grad_x, int64_t n_msgs, int n_vec,
+                              cudaStream_t stream) {
+    const int64_t items = ceil_div(n_msgs, kSegRun);
+#define B200MP_MS(G_) \
+    multi_aggr_backward_segment_kernel<I, G_><<<static_cast<unsigned>(ceil_div(items, 128 / G_)), 128, 0, stream>>>(idx, x, g, grad_x, n_msgs, n_vec)
+    if (n_vec <= 1) B200MP_MS(1);
+    else if (n_vec <= 2) B200MP_MS(2);
+    else if (n_vec <= 4) B200MP_MS(4);
+    else if (n_vec <= 8) B200MP_MS(8);
+    else if (n_vec <= 16) B200MP_MS(16);
+    else B200MP_MS(32);
+#undef B200MP_MS
+}
+
 template <typename T, typename I>
 int multi_bwd_typed(const void* ptr, const void* idx, const void* x, MultiGrad g, void* grad_x, int64_t n_items,
                     int64_t feat, int segment, cudaStream_t stream) {
@@ -948,8 +1024,8 @@ int multi_bwd_typed(const void* ptr, const void* idx, const void* x, MultiGrad g
     if (vec_ok) {
         const int n_vec = static_cast<int>(feat / 4);
         if (segment)
-            multi_bwd_vec_launch<I, true>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
-                                          static_cast<const float*>(x), g, static_cast<float*>(grad_x), n_items, n_vec, stream);
+            multi_bwd_segment_launch<I>(static_cast<const I*>(idx), static_cast<const float*>(x), g, static_cast<float*>(grad_x),
+                                        n_items, n_vec, stream);
         else if (g.hit_mask && n_vec > 16 && n_vec <= 64) {
             // (without the mask the staged form holds 4 rows x 2 destinations x 2 stages per thread = 64 KB per CTA; 12 warps
             //  per SM ran the sweep at 113 ms against 73 ms for the register form below at 24 -- measured, r2c_multi_*.json)

@@ -185,3 +185,24 @@ def test_multi_aggregation_modes():
         assert torch.equal(got, want), mode
     proj = MultiAggregation(["sum", "softmax"], mode="proj", mode_kwargs=dict(in_channels=F, out_channels=3)).to(DEV)
     assert proj(x, index, dim_size=N).shape == (N, 3)
+
+
+@pytest.mark.parametrize("F", [8, 64, 132])
+def test_segment_mode_backward_runs_of_messages(F):
+    """Segment mode (destination-sorted [E, F] messages, what MultiAggregation / PNAConv pass): the backward walks runs of 8
+    consecutive messages per lane group (E not a multiple of 8, runs that straddle several destinations)."""
+    rng = np.random.default_rng(F)
+    N, E = 900, 20011
+    index = np.sort(((rng.random(E) ** 2) * (N - 3)).astype(np.int64))
+    x = rng.standard_normal((E, F)).astype(np.float32)
+    x[rng.random((E, F)) < 0.2] = 0.0
+    aggrs = ["sum", "mean", "min", "max", "var", "std"]
+    xt = cu(x).requires_grad_()
+    idx = cu(index)
+    outs = Fn.multi_aggregate((ops.index2ptr(idx, N), idx, None), xt, aggrs)
+    ref = O.fused_aggregation(x, index, N, aggrs)
+    check_outputs(aggrs, outs, ref)
+    gouts = [rng.standard_normal((N, F)).astype(np.float32) for _ in aggrs]
+    torch.autograd.backward(outs, [cu(go) for go in gouts])
+    gmsg = O.fused_aggregation_backward(gouts, x, index, N, aggrs)
+    assert_close(npy(xt.grad), gmsg, rtol=2e-5, atol=2e-5 * max(1.0, np.abs(gmsg).max() / 10), msg="grad messages")
