@@ -849,17 +849,19 @@ template <typename T, typename I, bool GATHER, int MODE>
 void multi_launch_mode(const I* rowptr, const I* col, const T* x, const MultiOut& outs, int64_t n_rows, int n_vec,
                        const LongRowPlan& plan, cudaStream_t stream) {
     const int64_t items = plan.n_chunks + n_rows;
+    // one-warp CTAs (every mode holds >= 52 registers, so 32 resident CTAs per SM are never the limit): a CTA's slots are
+    // free as soon as ITS rows are done instead of after the longest row of four warps (power-law degrees); multi_tune 5 =
+    // the 128-thread form, kept for A/B
+    const int bt = get_option_multi_tune() == 5 ? 128 : 32;
 #define B200MP_MA(G_)                                                                                            \
-    multi_aggr_kernel<T, I, G_, GATHER, MODE><<<static_cast<unsigned>(ceil_div(items, 128 / G_)), 128, 0, stream>>>( \
+    multi_aggr_kernel<T, I, G_, GATHER, MODE><<<static_cast<unsigned>(ceil_div(items, bt / G_)), bt, 0, stream>>>( \
         rowptr, col, x, outs, n_rows, n_vec, plan)
     if (n_vec <= 1) B200MP_MA(1);
     else if (n_vec <= 2) B200MP_MA(2);
     else if (n_vec <= 4) B200MP_MA(4);
     else if (n_vec <= 8) B200MP_MA(8);
     else if (n_vec <= 16) B200MP_MA(16);
-    else if (get_option_multi_tune() == 5) B200MP_MA(32);
-    else                                       // a warp per row: one-warp CTAs, so a long row does not hold three idle warps' slots
-        multi_aggr_kernel<T, I, 32, GATHER, MODE><<<static_cast<unsigned>(items), 32, 0, stream>>>(rowptr, col, x, outs, n_rows, n_vec, plan);
+    else B200MP_MA(32);
 #undef B200MP_MA
 }
 
