@@ -356,6 +356,10 @@ int b200mp_spmm_csr_arg(const void* rowptr, const void* col, const float* val, c
  * queries): [n_rows, heads*chan], stride q_stride; s_src [n_src, heads], s_dst [n_rows, heads], att [heads*chan],
  * s_edge [n_edges, heads] (CSR order, nullable) fp32.  out [n_rows, heads*chan]; row_max / row_den [n_rows, heads]
  * fp32 are saved for the backward; alpha_out (nullable) [n_edges, heads] fp32 in CSR order.
+ * dropout_p in [0, 1): attention dropout (gat_conv.py:404, gatv2_conv.py:376, transformer_conv.py:268 -- F.dropout on the
+ * normalised coefficients): (edge, head) pairs are dropped by a counter-based hash of (dropout_seed, CSR slot, head) that the
+ * forward and the backward evaluate identically (pass the same p and seed to both); kept coefficients are scaled by
+ * 1 / (1 - p); alpha_out returns the dropped coefficients like the reference.  0 = no dropout.
  * Shapes: b200mp_attn_supported(heads, chan, val_dtype) != 0 (rows of whole 16-byte vectors, <= 1 KB, a head =
  * a power-of-two number of vectors), else B200MP_ERR_UNSUPPORTED.  Hub rows: the long-row plan of
  * b200mp_csr_plan_* plus part_acc [n_chunks, heads*chan] and part_ms [n_chunks, heads, 2] fp32.
@@ -372,8 +376,8 @@ int b200mp_attn_csr_forward(int mode, const void* rowptr, const void* col, const
                             void* out, float* row_max, float* row_den, float* alpha_out, int64_t n_rows,
                             int64_t n_edges, int64_t heads, int64_t chan, float slope, float scale,
                             const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
-                            int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, int idx_dtype,
-                            int val_dtype, void* stream);
+                            int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, float dropout_p,
+                            unsigned long long dropout_seed, int idx_dtype, int val_dtype, void* stream);
 int64_t b200mp_attn_backward_partial_width(int mode, int64_t heads, int64_t chan, int transposed);
 int64_t b200mp_attn_gatt_rows(void);
 int b200mp_attn_csr_backward(int mode, const void* rowptr, const void* col, const void* rowptr_t,
@@ -386,8 +390,8 @@ int b200mp_attn_csr_backward(int mode, const void* rowptr, const void* col, cons
                              int64_t heads, int64_t chan, float slope, float scale, const int64_t* long_rows,
                              const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks, int64_t chunk,
                              float* partials, const int64_t* long_rows_t, const int64_t* chunk_ptr_t,
-                             int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, int idx_dtype,
-                             int val_dtype, void* stream);
+                             int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, float dropout_p,
+                             unsigned long long dropout_seed, int idx_dtype, int val_dtype, void* stream);
 
 /* ------------------------------------------------------------------ dense transform on tensor cores
  * fp32-accurate 3xTF32 GEMMs (tcgen05 + TMEM + TMA, csrc/gemm_tf32x3.cu) for the layer's

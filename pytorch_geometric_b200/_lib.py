@@ -15,6 +15,7 @@ _I64 = ctypes.c_int64
 _INT = ctypes.c_int
 _P = ctypes.c_void_p
 _F = ctypes.c_float
+_U64 = ctypes.c_uint64
 
 # name -> (restype, argtypes); mirrors include/b200mp.h one to one
 _SIGS = {
@@ -61,11 +62,11 @@ _SIGS = {
     "b200mp_spmm_csr_arg": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _INT, _P]),
     "b200mp_attn_supported": (_INT, [_I64, _I64, _INT]),
     "b200mp_attn_csr_forward": (_INT, [_INT] + [_P] * 9 + [_I64] * 3 + [_P] * 4 + [_I64] * 4 + [_F, _F, _P, _P, _I64, _I64, _I64,
-                                       _P, _P, _INT, _INT, _P]),
+                                       _P, _P, _F, _U64, _INT, _INT, _P]),
     "b200mp_attn_backward_partial_width": (_I64, [_INT, _I64, _I64, _INT]),
     "b200mp_attn_gatt_rows": (_I64, []),
     "b200mp_attn_csr_backward": (_INT, [_INT] + [_P] * 12 + [_I64] * 3 + [_P] * 12 + [_I64] * 5 + [_F, _F, _P, _P, _I64, _I64,
-                                        _I64, _P, _P, _P, _I64, _I64, _P, _INT, _INT, _P]),
+                                        _I64, _P, _P, _P, _I64, _I64, _P, _F, _U64, _INT, _INT, _P]),
     "b200mp_column_sum_parts": (_I64, [_I64]),
     "b200mp_column_sum": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P]),
     "b200mp_softmax_edge_op": (_INT, [_INT, _P, _P, _P, _P, _P, _I64, _I64, _INT, _P]),

@@ -54,7 +54,24 @@ struct AttnArgs {
     size_t v_stride, k_stride, q_stride;   // row strides in BYTES (k and v may be halves of one [N, 2HC] matrix)
     int heads, chan, n_vec, lph;
     float slope, scale;
+    // attention dropout (gat_conv.py:404 `alpha = F.dropout(alpha, p, training)`): edge e, head h is dropped when
+    // hash(seed, e * H + h) < thresh; kept coefficients are scaled by 1 / (1 - p).  thresh = 0: no dropout.
+    uint32_t drop_thresh;
+    float drop_scale;
+    unsigned long long drop_seed;
 };
+
+// The same (edge, head) decision in the forward and in both backward sweeps: counter-based (splitmix64 of the CSR slot
+// and head), no state, no [E, H] mask tensor.  torch's Philox stream cannot be reproduced from inside a fused sweep;
+// tests compare against the unfused formula with THIS mask (read back through the returned attention coefficients).
+__device__ __forceinline__ float drop_factor(const AttnArgs& a, int64_t e, int head) {
+    if (a.drop_thresh == 0u) return 1.0f;
+    unsigned long long z = a.drop_seed + static_cast<unsigned long long>(e * a.heads + head) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return static_cast<uint32_t>(z >> 32) >= a.drop_thresh ? a.drop_scale : 0.0f;
+}
 
 __device__ __forceinline__ float leaky_f(float v, float slope) { return v > 0.0f ? v : v * slope; }
 
@@ -201,9 +218,10 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
                     const float mn = fmaxf(m[0], l);
                     const float rs = fexp(m[0] - mn);
                     const float p = fexp(l - mn);
-                    s[0] = fmaf(s[0], rs, p);
+                    s[0] = fmaf(s[0], rs, p);                           // the softmax denominator ignores dropout
+                    const float pk = p * drop_factor(a, begin + j, head[0]);
 #pragma unroll
-                    for (int i = 0; i < EPV; ++i) acc[0][i] = fmaf(acc[0][i], rs, p * f[i]);
+                    for (int i = 0; i < EPV; ++i) acc[0][i] = fmaf(acc[0][i], rs, pk * f[i]);
                     m[0] = mn;
                 }
             }
@@ -277,8 +295,9 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
                         const float rs = fexp(m[k] - mn);               // 0 on the first edge (m = -inf)
                         const float p = fexp(l[k] - mn);
                         s[k] = fmaf(s[k], rs, p);
+                        const float pk = p * drop_factor(a, b0 + j0 + u * S + sub, head[k]);
 #pragma unroll
-                        for (int i = 0; i < EPV; ++i) acc[k][i] = fmaf(acc[k][i], rs, p * f[k][i]);
+                        for (int i = 0; i < EPV; ++i) acc[k][i] = fmaf(acc[k][i], rs, pk * f[k][i]);
                         m[k] = mn;
                     }
                 }
@@ -502,11 +521,13 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
                 const float score = MODE == ATTN_GAT ? leaky_f(l[k], a.slope) : l[k];
                 const float alpha = fexp(score - mrow[k]) * inv_den[k];
                 const bool first = ((lig + k * G) * EPV) % a.chan == 0;
+                const float keep = drop_factor(a, e, head[k]);           // 0 or 1 / (1 - p); 1 without dropout
                 if (ALPHA_ONLY) {
-                    if (first) alpha_out[e * a.heads + head[k]] = alpha;
+                    if (first) alpha_out[e * a.heads + head[k]] = alpha * keep;    // the reference returns the dropped alpha
                     continue;
                 }
-                float gs = alpha * (dot[k] - D[k]);
+                // out = sum_e keep_e alpha_e v_e, D = <g, out>:  d/d score_e = alpha_e (keep_e <g, v_e> - D)
+                float gs = alpha * (keep * dot[k] - D[k]);
                 if (MODE == ATTN_GAT) {
                     gs *= (l[k] > 0.0f ? 1.0f : a.slope);
                     if (first) gsd[k] += gs;
@@ -524,7 +545,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
 #pragma unroll
                     for (int i = 0; i < EPV; ++i) gq[k][i] = fmaf(gs, kf[k][i], gq[k][i]);
                 }
-                if (first) *reinterpret_cast<float2*>(pair + (e * a.heads + head[k]) * 2) = make_float2(alpha, gs);
+                if (first) *reinterpret_cast<float2*>(pair + (e * a.heads + head[k]) * 2) = make_float2(alpha * keep, gs);
             }
         };
 
@@ -1097,8 +1118,12 @@ namespace {
 
 int fill_args(AttnArgs& a, int mode, const void* v, const void* k, const void* q, const float* s_src, const float* s_dst,
               const float* att, const float* s_edge, int64_t v_stride, int64_t k_stride, int64_t q_stride, int64_t heads,
-              int64_t chan, float slope, float scale, int val_dtype) {
+              int64_t chan, float slope, float scale, int val_dtype, float dropout_p, unsigned long long dropout_seed) {
     const size_t es = val_dtype == B200MP_BF16 ? 2 : 4;
+    if (!(dropout_p >= 0.0f && dropout_p < 1.0f)) return 1;
+    a.drop_thresh = dropout_p > 0.0f ? static_cast<uint32_t>(fmin(4294967295.0, ceil(static_cast<double>(dropout_p) * 4294967296.0))) : 0u;
+    a.drop_scale = dropout_p > 0.0f ? 1.0f / (1.0f - dropout_p) : 1.0f;
+    a.drop_seed = dropout_seed;
     const size_t hc_bytes = static_cast<size_t>(heads * chan) * es;
     a.v = static_cast<const char*>(v);
     a.k = static_cast<const char*>(k);
@@ -1165,7 +1190,7 @@ extern "C" int b200mp_attn_csr_forward(int mode, const void* rowptr, const void*
                                        void* out, float* row_max, float* row_den, float* alpha_out, int64_t n_rows,
                                        int64_t n_edges, int64_t heads, int64_t chan, float slope, float scale,
                                        const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
-                                       int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, int idx_dtype,
+                                       int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, float dropout_p, unsigned long long dropout_seed, int idx_dtype,
                                        int val_dtype, void* stream) {
     B200MP_CHECK_ARG(mode >= ATTN_GAT && mode <= ATTN_DOT);
     B200MP_CHECK_ARG(n_rows >= 0 && n_edges >= 0 && heads > 0 && chan > 0);
@@ -1173,8 +1198,8 @@ extern "C" int b200mp_attn_csr_forward(int mode, const void* rowptr, const void*
     B200MP_CHECK_ARG(rowptr && out && row_max && row_den && (n_edges == 0 || (col && v)));
     B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && part_acc && part_ms && chunk > 0));
     AttnArgs a;
-    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype)) {
-        set_error("attn forward: operands missing for mode %d", mode);
+    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype, dropout_p, dropout_seed)) {
+        set_error("attn forward: operands missing for mode %d (or dropout_p outside [0, 1))", mode);
         return B200MP_ERR_INVALID_ARG;
     }
     if (!b200mp_attn_supported(heads, chan, val_dtype) || !aligned16(v) || !aligned16(out) || a.v_stride % 16 || a.k_stride % 16 ||
@@ -1207,7 +1232,7 @@ extern "C" int b200mp_attn_csr_backward(int mode, const void* rowptr, const void
                                         int64_t chan, float slope, float scale, const int64_t* long_rows,
                                         const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks, int64_t chunk,
                                         float* partials, const int64_t* long_rows_t, const int64_t* chunk_ptr_t,
-                                        int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, int idx_dtype,
+                                        int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, float dropout_p, unsigned long long dropout_seed, int idx_dtype,
                                         int val_dtype, void* stream) {
     B200MP_CHECK_ARG(mode >= ATTN_GAT && mode <= ATTN_DOT);
     B200MP_CHECK_ARG(n_rows >= 0 && n_src >= 0 && n_edges >= 0 && heads > 0 && chan > 0);
@@ -1220,8 +1245,8 @@ extern "C" int b200mp_attn_csr_backward(int mode, const void* rowptr, const void
     B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && partials && chunk > 0));
     B200MP_CHECK_ARG(n_long_rows_t == 0 || (long_rows_t && chunk_ptr_t && partials_t && chunk > 0));
     AttnArgs a;
-    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype)) {
-        set_error("attn backward: operands missing for mode %d", mode);
+    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype, dropout_p, dropout_seed)) {
+        set_error("attn backward: operands missing for mode %d (or dropout_p outside [0, 1))", mode);
         return B200MP_ERR_INVALID_ARG;
     }
     if (!b200mp_attn_supported(heads, chan, val_dtype) || !aligned16(v) || !aligned16(out) || !aligned16(grad_out) || !aligned16(grad_v) ||

@@ -238,7 +238,8 @@ def _finish_heads(out: Tensor, H: int, C: int, concat: bool, res: Optional[Tenso
 
 def gat_conv(xh_src: Tensor, xh_dst: Optional[Tensor], graph: CSRGraph, att_src: Tensor, att_dst: Optional[Tensor], H: int,
              C: int, negative_slope: float = 0.2, concat: bool = True, res: Optional[Tensor] = None,
-             bias: Optional[Tensor] = None, s_edge: Optional[Tensor] = None, return_alpha: bool = False):
+             bias: Optional[Tensor] = None, s_edge: Optional[Tensor] = None, return_alpha: bool = False,
+             dropout_p: float = 0.0):
     """GATConv after its linear maps (gat_conv.py:330-385): xh_* = lin(x) [n, H*C]; xh_dst None = the sources are the
     destinations; att_dst None = no destination term (x = (x_src, None)).  s_edge [E, H] =
     (lin_edge(edge_attr) * att_edge).sum(-1) aligned with the edges the graph was built from (edge_dim)."""
@@ -251,27 +252,30 @@ def gat_conv(xh_src: Tensor, xh_dst: Optional[Tensor], graph: CSRGraph, att_src:
         a_src = _head_dot(xh_src, att_src, H, C)
         a_dst = _head_dot(xh_dst, att_dst, H, C)
     r = Fn.attention("gat", graph, H, C, v=xh_src, s_src=a_src, s_dst=a_dst, s_edge=s_edge, negative_slope=negative_slope,
-                     return_alpha=return_alpha)
+                     return_alpha=return_alpha, dropout_p=dropout_p)
     out, alpha = r if return_alpha else (r, None)
     out = _finish_heads(out, H, C, concat, res, bias)
     return (out, alpha) if return_alpha else out
 
 
 def gatv2_conv(x_l: Tensor, x_r: Tensor, graph: CSRGraph, att: Tensor, H: int, C: int, negative_slope: float = 0.2,
-               concat: bool = True, res: Optional[Tensor] = None, bias: Optional[Tensor] = None, return_alpha: bool = False):
+               concat: bool = True, res: Optional[Tensor] = None, bias: Optional[Tensor] = None, return_alpha: bool = False,
+               dropout_p: float = 0.0):
     """GATv2Conv after lin_l / lin_r (gatv2_conv.py:300-331, 356-378): x_l [n_src, H*C], x_r [n_dst, H*C]."""
     r = Fn.attention("gatv2", graph, H, C, v=x_l, q=x_r, att=att.reshape(-1), negative_slope=negative_slope,
-                     return_alpha=return_alpha)
+                     return_alpha=return_alpha, dropout_p=dropout_p)
     out, alpha = r if return_alpha else (r, None)
     out = _finish_heads(out, H, C, concat, res, bias)
     return (out, alpha) if return_alpha else out
 
 
 def transformer_conv(query: Tensor, kv: Tensor, graph: CSRGraph, H: int, C: int, concat: bool = True,
-                     x_skip: Optional[Tensor] = None, w_beta: Optional[Tensor] = None, return_alpha: bool = False):
+                     x_skip: Optional[Tensor] = None, w_beta: Optional[Tensor] = None, return_alpha: bool = False,
+                     dropout_p: float = 0.0):
     """TransformerConv after its linear maps (transformer_conv.py:222-275): query [n_dst, H*C], kv [n_src, 2*H*C]
     (keys | values from ONE product with the concatenated lin_key / lin_value weights); x_skip = lin_skip(x_dst)."""
-    r = Fn.attention("dot", graph, H, C, q=query, kv=kv, scale=1.0 / math.sqrt(C), return_alpha=return_alpha)
+    r = Fn.attention("dot", graph, H, C, q=query, kv=kv, scale=1.0 / math.sqrt(C), return_alpha=return_alpha,
+                     dropout_p=dropout_p)
     out, alpha = r if return_alpha else (r, None)
     if not concat:
         out = out.view(-1, H, C).mean(dim=1)
@@ -535,8 +539,9 @@ def edge_attr_with_loops(edge_index: Tensor, edge_attr: Tensor, num_nodes: int, 
 
 class GATConv(torch.nn.Module):
     """Mirror of torch_geometric.nn.GATConv (nn/conv/gat_conv.py:27-413) incl. bipartite inputs and `edge_dim`;
-    attention + aggregation run in the fused kernel (csrc/attention.cu).  Attention dropout (training-time,
-    gat_conv.py:405) is not fused: dropout must be 0 (or the module in eval mode)."""
+    attention + aggregation run in the fused kernel (csrc/attention.cu), attention dropout (training-time,
+    gat_conv.py:404) included: the kept (edge, head) pairs come from a counter-based hash seeded from torch's CPU generator
+    -- the same distribution as F.dropout, not the same random stream."""
 
     def __init__(self, in_channels, out_channels: int, heads: int = 1, concat: bool = True, negative_slope: float = 0.2,
                  dropout: float = 0.0, add_self_loops: bool = True, edge_dim: Optional[int] = None, fill_value="mean",
@@ -572,8 +577,7 @@ class GATConv(torch.nn.Module):
 
     def forward(self, x, edge_index: Adj, edge_attr: Optional[Tensor] = None, size=None,
                 return_attention_weights: Optional[bool] = None):
-        if self.dropout != 0.0 and self.training:
-            raise NotImplementedError("attention dropout is not fused; use dropout=0 or eval()")
+        drop = float(self.dropout) if self.training else 0.0        # attention dropout runs inside the sweep
         H, C = self.heads, self.out_channels
         att_dst = self.att_dst
         if isinstance(x, Tensor):
@@ -606,7 +610,7 @@ class GATConv(torch.nn.Module):
             s_edge = _head_dot(self.lin_edge(ea), self.att_edge, H, C)
         want = return_attention_weights is not None
         r = gat_conv(xh_src, xh_dst, graph, self.att_src, att_dst, H, C, self.negative_slope, self.concat, res, self.bias,
-                     s_edge, want)
+                     s_edge, want, drop)
         if want:
             out, alpha = r
             ei = torch.stack([graph.col.long(), graph.dst_csr.long()])         # alpha is in the engine's CSR order
@@ -618,7 +622,7 @@ class GATConv(torch.nn.Module):
 
 
 class GATv2Conv(torch.nn.Module):
-    """Mirror of torch_geometric.nn.GATv2Conv (nn/conv/gatv2_conv.py:24-385) without edge_dim / dropout: the score
+    """Mirror of torch_geometric.nn.GATv2Conv (nn/conv/gatv2_conv.py:24-385) without edge_dim: the score
     att . leaky_relu(x_l[j] + x_r[i]), the edge softmax and the aggregation are ONE sweep (csrc/attention.cu)."""
 
     def __init__(self, in_channels, out_channels: int, heads: int = 1, concat: bool = True, negative_slope: float = 0.2,
@@ -641,8 +645,7 @@ class GATv2Conv(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros(total)) if bias else None
 
     def forward(self, x, edge_index: Adj, edge_attr=None, return_attention_weights: Optional[bool] = None):
-        if self.dropout != 0.0 and self.training:
-            raise NotImplementedError("attention dropout is not fused; use dropout=0 or eval()")
+        drop = float(self.dropout) if self.training else 0.0        # attention dropout runs inside the sweep
         if edge_attr is not None:
             raise NotImplementedError("edge_attr is not on the fused GATv2 path")
         H, C = self.heads, self.out_channels
@@ -656,7 +659,7 @@ class GATv2Conv(torch.nn.Module):
             x_r = self.lin_r(x[1])
         graph = _attention_graph(edge_index, x_l.size(0), x_r.size(0), self.add_self_loops, self.flow)
         want = return_attention_weights is not None
-        r = gatv2_conv(x_l, x_r, graph, self.att, H, C, self.negative_slope, self.concat, res, self.bias, want)
+        r = gatv2_conv(x_l, x_r, graph, self.att, H, C, self.negative_slope, self.concat, res, self.bias, want, drop)
         if want:
             out, alpha = r
             return out, (torch.stack([graph.col.long(), graph.dst_csr.long()]), alpha)
@@ -667,7 +670,7 @@ class GATv2Conv(torch.nn.Module):
 
 
 class TransformerConv(torch.nn.Module):
-    """Mirror of torch_geometric.nn.TransformerConv (nn/conv/transformer_conv.py:17-285) without edge_dim / dropout:
+    """Mirror of torch_geometric.nn.TransformerConv (nn/conv/transformer_conv.py:17-285) without edge_dim:
     q.k / sqrt(C) scores, edge softmax and the value aggregation in ONE sweep; keys and values come from one GEMM
     with the concatenated lin_key / lin_value weights and are read as the two halves of one [N, 2HC] matrix."""
 
@@ -689,8 +692,7 @@ class TransformerConv(torch.nn.Module):
         self.lin_beta = _Lin(3 * total, 1, bias=False) if self.beta else None
 
     def forward(self, x, edge_index: Adj, edge_attr=None, return_attention_weights: Optional[bool] = None):
-        if self.dropout != 0.0 and self.training:
-            raise NotImplementedError("attention dropout is not fused; use dropout=0 or eval()")
+        drop = float(self.dropout) if self.training else 0.0        # attention dropout runs inside the sweep
         if edge_attr is not None:
             raise NotImplementedError("edge_attr is not on the fused TransformerConv path")
         H, C = self.heads, self.out_channels
@@ -702,7 +704,7 @@ class TransformerConv(torch.nn.Module):
         graph = _plain_graph(edge_index, x[0].size(0), x[1].size(0), self.flow)
         x_skip = self.lin_skip(x[1]) if self.root_weight else None
         want = isinstance(return_attention_weights, bool)
-        r = transformer_conv(query, kv, graph, H, C, self.concat, x_skip, _w(self.lin_beta), want)
+        r = transformer_conv(query, kv, graph, H, C, self.concat, x_skip, _w(self.lin_beta), want, drop)
         if want:
             out, alpha = r
             return out, (torch.stack([graph.col.long(), graph.dst_csr.long()]), alpha)

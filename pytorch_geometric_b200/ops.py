@@ -560,9 +560,10 @@ def _row_stride(t: Optional[Tensor], hc: int) -> int:
 def attn_forward(mode: str, rowptr: Tensor, col: Tensor, v: Tensor, heads: int, chan: int, *, k: Optional[Tensor] = None,
                  q: Optional[Tensor] = None, s_src: Optional[Tensor] = None, s_dst: Optional[Tensor] = None,
                  att: Optional[Tensor] = None, s_edge: Optional[Tensor] = None, slope: float = 0.2, scale: float = 1.0,
-                 want_alpha: bool = False, plan: Optional["LongRowPlan"] = None):
+                 want_alpha: bool = False, plan: Optional["LongRowPlan"] = None, dropout_p: float = 0.0, dropout_seed: int = 0):
     """Fused edge-softmax attention + aggregation (b200mp_attn_csr_forward).  v / k: [n_src, H*C] (column slices of
-    a wider matrix are fine), q: [n_rows, H*C].  Returns (out, row_max, row_den, alpha or None)."""
+    a wider matrix are fine), q: [n_rows, H*C].  Returns (out, row_max, row_den, alpha or None).
+    dropout_p / dropout_seed: attention dropout fused into the sweep (pass the same pair to attn_backward)."""
     _cuda(rowptr, col, v, k, q, s_src, s_dst, att, s_edge)
     it = _same_idx(rowptr, col)
     hc = heads * chan
@@ -577,14 +578,14 @@ def attn_forward(mode: str, rowptr: Tensor, col: Tensor, v: Tensor, heads: int, 
     _timed("attn_forward", launches, lib().b200mp_attn_csr_forward, ATTN_MODES[mode], _p(rowptr), _p(col), _p(v), _p(k), _p(q),
            _p(s_src), _p(s_dst), _p(att), _p(s_edge), _row_stride(v, hc), _row_stride(k, hc), _row_stride(q, hc), _p(out),
            _p(row_max), _p(row_den), _p(alpha), n_rows, col.numel(), heads, chan, float(slope), float(scale), *pargs,
-           _p(part_ms), it, _vdt(v), _stream())
+           _p(part_ms), float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, it, _vdt(v), _stream())
     return out, row_max, row_den, alpha
 
 
 def attn_backward(mode: str, rowptr, col, rowptr_t, col_t, t2csr, v: Tensor, heads: int, chan: int, row_max, row_den, out,
                   grad_out, *, k=None, q=None, s_src=None, s_dst=None, att=None, s_edge=None, slope: float = 0.2,
                   scale: float = 1.0, plan=None, plan_t=None, grad_v: Optional[Tensor] = None,
-                  grad_k: Optional[Tensor] = None):
+                  grad_k: Optional[Tensor] = None, dropout_p: float = 0.0, dropout_seed: int = 0):
     """Backward of attn_forward.  Returns a dict with grad_v, and per mode grad_k / grad_q / grad_s_src /
     grad_s_dst / grad_att / grad_s_edge.  grad_v / grad_k may be preallocated (column slices of one matrix)."""
     _cuda(rowptr, col, rowptr_t, col_t, t2csr, v, grad_out)
@@ -622,7 +623,7 @@ def attn_backward(mode: str, rowptr, col, rowptr_t, col_t, t2csr, v: Tensor, hea
            _p(s_edge), _row_stride(v, hc), _row_stride(k, hc), _row_stride(q, hc), _p(row_max), _p(row_den), _p(out),
            _p(grad_out), _p(pair), _p(grad_v), _p(grad_k), _p(grad_q), _p(gss), _p(gsd), _p(gatt), _p(gatt_part), n_rows,
            n_src, n_edges, heads, chan, float(slope), float(scale), pa[0], pa[1], pa[2], pa[3], pa[4], pa[5], pt[0],
-           pt[1], pt[2], pt[3], pt[5], it, _vdt(v), _stream())
+           pt[1], pt[2], pt[3], pt[5], float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, it, _vdt(v), _stream())
     res = {"grad_v": grad_v, "grad_k": grad_k, "grad_q": grad_q, "grad_s_src": gss, "grad_s_dst": gsd, "grad_att": gatt}
     if s_edge is not None:
         res["grad_s_edge"] = pair[:, :, 1]

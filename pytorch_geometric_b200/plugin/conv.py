@@ -11,7 +11,7 @@ through the routed `scatter` / `softmax` / lazy gather).  `message_and_aggregate
 
 A fall-through happens for: CPU / other dtypes, `explain=True`, `decomposed_layers > 1`, any registered
 propagate / message / aggregate hook (message_passing.py:776-922), `SparseTensor` / `torch.sparse` adjacencies,
-attention dropout in training mode, and layer options the kernels do not cover.
+and layer options the kernels do not cover.  Attention dropout (training mode) runs inside the fused sweep.
 """
 from __future__ import annotations
 
@@ -167,7 +167,12 @@ class B200GINConv(_FusedEdgeIndexMixin, tgnn.GINConv):
 
 
 def _attn_fast(self, *tensors) -> bool:
-    return _fast(self, *tensors) and not (self.dropout > 0.0 and self.training)
+    return _fast(self, *tensors)
+
+
+def _drop(self) -> float:
+    """Attention dropout runs inside the fused sweep (same distribution as F.dropout, its own random stream)."""
+    return float(self.dropout) if self.training else 0.0
 
 
 class B200GATConv(tgnn.GATConv):
@@ -196,7 +201,7 @@ class B200GATConv(tgnn.GATConv):
                 s_edge = C._head_dot(dense.linear(ea, self.lin_edge.weight), self.att_edge, H, Cc)
             att_dst = self.att_dst if (xs[1] is not None) else None
             return C.gat_conv(xh_src, xh_dst, g, self.att_src, att_dst, H, Cc, self.negative_slope, self.concat, res,
-                              self.bias, s_edge, False)
+                              self.bias, s_edge, False, _drop(self))
         return super().forward(x, edge_index, edge_attr, size, return_attention_weights)
 
 
@@ -214,7 +219,8 @@ class B200GATv2Conv(tgnn.GATv2Conv):
                 x_r = dense.linear(xs[1], self.lin_r.weight, self.lin_r.bias)
             g = cached_graph(_plain(edge_index), x_l.size(0), x_r.size(0), flow=self.flow,
                              loops="gat" if self.add_self_loops else None, loop_nodes=min(x_l.size(0), x_r.size(0)))
-            return C.gatv2_conv(x_l, x_r, g, self.att, H, Cc, self.negative_slope, self.concat, res, self.bias, False)
+            return C.gatv2_conv(x_l, x_r, g, self.att, H, Cc, self.negative_slope, self.concat, res, self.bias, False,
+                                _drop(self))
         return super().forward(x, edge_index, edge_attr, return_attention_weights)
 
 
@@ -232,7 +238,7 @@ class B200TransformerConv(tgnn.TransformerConv):
             g = _graph(edge_index, xs[0].size(0), xs[1].size(0), self.flow)
             x_skip = dense.linear(xs[1], self.lin_skip.weight, self.lin_skip.bias) if self.root_weight else None
             w_beta = self.lin_beta.weight if self.lin_beta is not None else None
-            return C.transformer_conv(query, kv, g, H, Cc, self.concat, x_skip, w_beta, False)
+            return C.transformer_conv(query, kv, g, H, Cc, self.concat, x_skip, w_beta, False, _drop(self))
         return super().forward(x, edge_index, edge_attr, return_attention_weights)
 
 

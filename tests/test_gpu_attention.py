@@ -24,7 +24,7 @@ DEV = "cuda"
 
 
 def ref_attention(mode, src, dst, n_dst, H, C, v, k=None, q=None, s_src=None, s_dst=None, att=None, s_edge=None,
-                  slope=0.2, scale=1.0):
+                  slope=0.2, scale=1.0, keep=None):
     vj = v[src].view(-1, H, C)
     if mode == "gat":
         pre = s_src[src] + s_dst[dst]
@@ -40,6 +40,8 @@ def ref_attention(mode, src, dst, n_dst, H, C, v, k=None, q=None, s_src=None, s_
     ex = (s - smax[dst]).exp()
     den = torch.zeros(n_dst, H, dtype=s.dtype, device=s.device).index_add(0, dst, ex) + 1e-16
     alpha = ex / den[dst]
+    if keep is not None:                                   # F.dropout(alpha): kept coefficients scaled by 1 / (1 - p)
+        alpha = alpha * keep
     out = torch.zeros(n_dst, H, C, dtype=s.dtype, device=s.device).index_add(0, dst, alpha.unsqueeze(-1) * vj)
     return out.view(n_dst, H * C), alpha
 
@@ -199,3 +201,84 @@ def test_head_dot_terms_and_their_backward(H, C, dtype, pair):
     for got, ref in ((att_a.grad, a64.grad), ) + (((att_b.grad, b64.grad), ) if pair else ()):
         assert got.shape == ref.shape
         assert float((got.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max() + N ** 0.5)
+
+
+@pytest.mark.parametrize("chunk", [512, 16])
+@pytest.mark.parametrize("mode,H,C,dtype", [("gat", 8, 16, torch.float32), ("gat", 8, 16, torch.bfloat16), ("gatv2", 4, 8, torch.float32),
+                                            ("dot", 2, 128, torch.float32), ("gat", 3, 4, torch.float32)])
+def test_attention_dropout_inside_the_sweep(mode, H, C, dtype, chunk):
+    """F.dropout(alpha, p, training) (gat_conv.py:404, gatv2_conv.py:376, transformer_conv.py:268) fused into the sweeps.
+    torch's random stream cannot be reproduced inside a kernel, so: (1) the dropped coefficients the engine returns are
+    alpha / (1 - p) or 0, with a keep rate of 1 - p, the same for the same seed and different for another seed;
+    (2) out and every gradient equal the unfused fp64 formula evaluated with THAT mask."""
+    p = _problem(mode, H, C, dtype, seed=H * 17 + C + len(mode))
+    n_src, n_dst = p["v"].size(0), p["gout"].size(0)
+    names = [n for n in ("v", "k", "q", "s_src", "s_dst", "att") if n in p]
+    scale = 1.0 / math.sqrt(C)
+    graph = CSRGraph(p["src"].to(DEV), p["dst"].to(DEV), n_src, n_dst, chunk=chunk)
+    perm = graph.perm.long()
+    feat = ("v", "k", "q")
+    ours = {n: (p[n].to(dtype) if n in feat else p[n].float()).to(DEV).requires_grad_() for n in names}
+    pd = 0.4
+    kw = dict(negative_slope=0.2, scale=scale, return_alpha=True)
+    with torch.no_grad():
+        _, alpha0 = Fn.attention(mode, graph, H, C, **kw, **ours)
+        _, alpha_b = Fn.attention(mode, graph, H, C, dropout_p=pd, dropout_seed=99, **kw, **ours)
+        _, alpha_c = Fn.attention(mode, graph, H, C, dropout_p=pd, dropout_seed=7, **kw, **ours)
+    out, alpha_d = Fn.attention(mode, graph, H, C, dropout_p=pd, dropout_seed=7, **kw, **ours)
+    assert torch.equal(alpha_c, alpha_d) and not torch.equal(alpha_b, alpha_d)
+    kept = alpha_d != 0
+    live = alpha0 > 1e-30
+    rate = (kept & live).sum().item() / live.sum().item()
+    assert abs(rate - (1 - pd)) < 0.02, rate
+    assert torch.allclose(alpha_d[kept], alpha0[kept] / (1 - pd), rtol=1e-6, atol=0)
+    per_head = (kept & live).float().sum(0) / live.float().sum(0)
+    assert float((per_head - (1 - pd)).abs().max()) < 0.05                    # heads draw independent masks
+    out.backward(p["gout"].to(dtype).to(DEV))
+    # the unfused formula with this mask (CSR order -> the caller's edge order)
+    keep = torch.empty_like(alpha_d, dtype=torch.float64)
+    keep[perm] = kept.double() / (1 - pd)
+    ref_in = {n: p[n].clone().to(DEV).requires_grad_() for n in names}
+    ref_out, _ = ref_attention(mode, p["src"].to(DEV), p["dst"].to(DEV), n_dst, H, C, slope=0.2, scale=scale, keep=keep, **ref_in)
+    ref_out.backward(p["gout"].to(DEV))
+    fp32 = dtype == torch.float32
+
+    def close(a, b, what, t):
+        a, b = a.detach().double(), b.detach().double()
+        err = (a - b).abs().max().item()
+        assert err <= t * max(b.abs().max().item(), 1e-3), f"{what}: max err {err:.3e} (scale {b.abs().max().item():.3e})"
+
+    close(out, ref_out, "out", 2e-5 if fp32 else 1.5e-2)
+    for n in names:
+        close(ours[n].grad, ref_in[n].grad, "grad_" + n, 2e-4 if fp32 else 3e-2)
+
+
+def test_attention_layers_train_with_dropout():
+    """The layers no longer refuse dropout > 0 in training mode; eval mode is deterministic and equals dropout = 0."""
+    from pytorch_geometric_b200.nn import GATConv, GATv2Conv, TransformerConv
+    torch.manual_seed(3)
+    N, E = 500, 6000
+    ei = torch.randint(0, N, (2, E), device=DEV)
+    x = torch.randn(N, 32, device=DEV)
+    for cls in (GATConv, GATv2Conv, TransformerConv):
+        torch.manual_seed(11)
+        a = cls(32, 16, heads=4, dropout=0.5).to(DEV)
+        torch.manual_seed(11)
+        b = cls(32, 16, heads=4, dropout=0.0).to(DEV)
+        b.load_state_dict(a.state_dict())
+        a.train()
+        torch.manual_seed(5)
+        y1 = a(x, ei)
+        torch.manual_seed(5)
+        y2 = a(x, ei)
+        y3 = a(x, ei)
+        assert torch.equal(y1, y2) and not torch.equal(y1, y3)                  # seeded from torch's generator
+        y1.sum().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in a.parameters())
+        a.eval(), b.eval()
+        assert torch.equal(a(x, ei), b(x, ei))
+        # E[dropout output] = no-dropout output: the mean over draws approaches the deterministic layer
+        a.train()
+        mean = torch.stack([a(x, ei) for _ in range(200)]).mean(0)
+        ref = b(x, ei)
+        assert float((mean - ref).abs().mean() / ref.abs().mean()) < 0.08, cls.__name__
