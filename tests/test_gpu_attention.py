@@ -279,6 +279,8 @@ def test_attention_layers_train_with_dropout():
         assert torch.equal(a(x, ei), b(x, ei))
         # E[dropout output] = no-dropout output: the mean over draws approaches the deterministic layer
         a.train()
-        mean = torch.stack([a(x, ei) for _ in range(200)]).mean(0)
-        ref = b(x, ei)
-        assert float((mean - ref).abs().mean() / ref.abs().mean()) < 0.08, cls.__name__
+        with torch.no_grad():
+            g = a.graph_for(ei, N) if hasattr(a, "graph_for") else ei          # (GATConv: build the CSR once)
+            mean = torch.stack([a(x, g) for _ in range(100)]).mean(0)
+            ref = b(x, ei)
+        assert float((mean - ref).abs().mean() / ref.abs().mean()) < 0.1, cls.__name__
