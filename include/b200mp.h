@@ -360,6 +360,10 @@ int b200mp_spmm_csr_arg(const void* rowptr, const void* col, const float* val, c
  * normalised coefficients): (edge, head) pairs are dropped by a counter-based hash of (dropout_seed, CSR slot, head) that the
  * forward and the backward evaluate identically (pass the same p and seed to both); kept coefficients are scaled by
  * 1 / (1 - p); alpha_out returns the dropped coefficients like the reference.  0 = no dropout.
+ * edge_feat (nullable; GATv2 and dot modes): per-edge feature rows [n_edges, heads*chan] of val_dtype in CSR order, i.e.
+ * lin_edge(edge_attr) of `edge_dim` layers: GATv2 adds them inside the leaky_relu (gatv2_conv.py:358-360), the dot mode to
+ * the key and to the value (transformer_conv.py:258-272).  The backward writes grad_edge_feat (same shape; required when
+ * edge_feat is given).  (GAT's edge_dim term is the scalar s_edge.)
  * Shapes: b200mp_attn_supported(heads, chan, val_dtype) != 0 (rows of whole 16-byte vectors, <= 1 KB, a head =
  * a power-of-two number of vectors), else B200MP_ERR_UNSUPPORTED.  Hub rows: the long-row plan of
  * b200mp_csr_plan_* plus part_acc [n_chunks, heads*chan] and part_ms [n_chunks, heads, 2] fp32.
@@ -377,7 +381,8 @@ int b200mp_attn_csr_forward(int mode, const void* rowptr, const void* col, const
                             int64_t n_edges, int64_t heads, int64_t chan, float slope, float scale,
                             const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
                             int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, float dropout_p,
-                            unsigned long long dropout_seed, int idx_dtype, int val_dtype, void* stream);
+                            unsigned long long dropout_seed, const void* edge_feat, int idx_dtype, int val_dtype,
+                            void* stream);
 int64_t b200mp_attn_backward_partial_width(int mode, int64_t heads, int64_t chan, int transposed);
 int64_t b200mp_attn_gatt_rows(void);
 int b200mp_attn_csr_backward(int mode, const void* rowptr, const void* col, const void* rowptr_t,
@@ -391,7 +396,8 @@ int b200mp_attn_csr_backward(int mode, const void* rowptr, const void* col, cons
                              const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks, int64_t chunk,
                              float* partials, const int64_t* long_rows_t, const int64_t* chunk_ptr_t,
                              int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, float dropout_p,
-                             unsigned long long dropout_seed, int idx_dtype, int val_dtype, void* stream);
+                             unsigned long long dropout_seed, const void* edge_feat, void* grad_edge_feat, int idx_dtype,
+                             int val_dtype, void* stream);
 
 /* ------------------------------------------------------------------ dense transform on tensor cores
  * fp32-accurate 3xTF32 GEMMs (tcgen05 + TMEM + TMA, csrc/gemm_tf32x3.cu) for the layer's

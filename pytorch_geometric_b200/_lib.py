@@ -62,11 +62,11 @@ _SIGS = {
     "b200mp_spmm_csr_arg": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _INT, _P]),
     "b200mp_attn_supported": (_INT, [_I64, _I64, _INT]),
     "b200mp_attn_csr_forward": (_INT, [_INT] + [_P] * 9 + [_I64] * 3 + [_P] * 4 + [_I64] * 4 + [_F, _F, _P, _P, _I64, _I64, _I64,
-                                       _P, _P, _F, _U64, _INT, _INT, _P]),
+                                       _P, _P, _F, _U64, _P, _INT, _INT, _P]),
     "b200mp_attn_backward_partial_width": (_I64, [_INT, _I64, _I64, _INT]),
     "b200mp_attn_gatt_rows": (_I64, []),
     "b200mp_attn_csr_backward": (_INT, [_INT] + [_P] * 12 + [_I64] * 3 + [_P] * 12 + [_I64] * 5 + [_F, _F, _P, _P, _I64, _I64,
-                                        _I64, _P, _P, _P, _I64, _I64, _P, _F, _U64, _INT, _INT, _P]),
+                                        _I64, _P, _P, _P, _I64, _I64, _P, _F, _U64, _P, _P, _INT, _INT, _P]),
     "b200mp_column_sum_parts": (_I64, [_I64]),
     "b200mp_column_sum": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P]),
     "b200mp_softmax_edge_op": (_INT, [_INT, _P, _P, _P, _P, _P, _I64, _I64, _INT, _P]),

@@ -51,6 +51,9 @@ struct AttnArgs {
     const float* s_dst;       // GAT a_dst [n_dst, H]
     const float* att;         // GATv2 att [H*C]
     const float* s_edge;      // GAT optional additive score [E, H] in CSR order (edge_dim)
+    const char* ee;           // GATv2 / DOT optional per-edge feature rows [E, H*C] in CSR order (edge_dim): GATv2 adds them
+                              // inside the leaky_relu (gatv2_conv.py:358-360), DOT to the key AND the value (transformer_conv.py:258-272)
+    char* grad_ee;            // backward: their gradient [E, H*C] (written by the destination sweep, read by GATv2's source sweep)
     size_t v_stride, k_stride, q_stride;   // row strides in BYTES (k and v may be halves of one [N, 2HC] matrix)
     int heads, chan, n_vec, lph;
     float slope, scale;
@@ -101,14 +104,16 @@ __device__ __forceinline__ void merge_ms(float m1, float m2, float& M, float& c1
 // same register budget (the sweeps are latency-bound: 58 % long-scoreboard stalls in profiles/r2_attn_v2.summary.csv).
 // BT = threads per CTA.  32 (one warp = one work item per CTA) for the staged kernels: a 4-warp CTA holds its slots until
 // the longest of its four power-law rows is done (ncu, r2_attn_v3: 35 % achieved of 50 % theoretical occupancy).
-template <typename T, typename I, int G, int VPL, int MODE, bool STAGED = false, int BT = kAttnT>
-__global__ void __launch_bounds__(BT, (VPL == 1 ? 8 : 5) * (kAttnT / BT))       // <= 64 registers: 32 warps / SM
+// VAR: 0 = rows gathered into registers, 1 = STAGED (cp.async slots), 2 = EDGE (register form + per-edge feature rows a.ee).
+template <typename T, typename I, int G, int VPL, int MODE, int VAR = 0, int BT = kAttnT>
+__global__ void __launch_bounds__(BT, (VPL == 1 ? (VAR == 2 ? 6 : 8) : 5) * (kAttnT / BT))       // <= 64 registers: 32 warps / SM
 attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArgs a, T* __restrict__ out,
                 float* __restrict__ row_max, float* __restrict__ row_den, int64_t n_rows, LongRowPlan plan,
                 float* __restrict__ part_ms) {
     constexpr int EPV = ElemTraits<T>::kPerVec;
     constexpr int S = 32 / G;
     constexpr int UNR = VPL == 1 ? 4 : 2;
+    constexpr bool STAGED = VAR == 1, EDGE = VAR == 2 && MODE != ATTN_GAT;
     const int lane = threadIdx.x & 31;
     const int lig = lane & (G - 1);
     const int sub = lane / G;
@@ -236,7 +241,7 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
         const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
         c_next = (b0 + 32 + lane < end) ? ldg_idx(col + b0 + 32 + lane) : I(0);
         for (int j0 = 0; j0 < nb; j0 += S * UNR) {
-            Vec16 vb[UNR][VPL], kb[UNR][VPL];
+            Vec16 vb[UNR][VPL], kb[UNR][VPL], eb[UNR][VPL];
             float sc[UNR][VPL];
             bool ev[UNR];
 #pragma unroll
@@ -251,6 +256,7 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
                         if (!valid[k]) continue;
                         const size_t off = static_cast<size_t>(lig + k * G) * 16;
                         vb[u][k] = ldg_row16(a.v + static_cast<size_t>(c) * a.v_stride + off);
+                        if (EDGE) eb[u][k] = ldg_stream16(a.ee + static_cast<size_t>(e) * (static_cast<size_t>(a.n_vec) * 16) + off);
                         if (MODE == ATTN_DOT) kb[u][k] = ldg_row16(a.k + static_cast<size_t>(c) * a.k_stride + off);
                         if (MODE == ATTN_GAT) {
                             sc[u][k] = __ldg(a.s_src + c * a.heads + head[k]);
@@ -266,17 +272,27 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
                 for (int k = 0; k < VPL; ++k) {
                     l[k] = 0.0f;
                     if (ev[u] && valid[k]) {
+                        float ef[EPV];
                         ElemTraits<T>::unpack(vb[u][k], f[k]);
+                        if (EDGE) {
+                            ElemTraits<T>::unpack(eb[u][k], ef);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < EPV; ++i) ef[i] = 0.0f;
+                        }
                         if (MODE == ATTN_GAT) l[k] = leaky_f(sc[u][k] + sd[k], a.slope);
                         if (MODE == ATTN_GATV2) {
 #pragma unroll
-                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i], a.slope), l[k]);
+                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i] + ef[i], a.slope), l[k]);
                         }
                         if (MODE == ATTN_DOT) {
                             float kf[EPV];
                             ElemTraits<T>::unpack(kb[u][k], kf);
 #pragma unroll
-                            for (int i = 0; i < EPV; ++i) l[k] = fmaf(qv[k][i], kf[i], l[k]);
+                            for (int i = 0; i < EPV; ++i) {
+                                l[k] = fmaf(qv[k][i], kf[i] + ef[i], l[k]);      // key_j + e
+                                f[k][i] += ef[i];                                // value_j + e
+                            }
                         }
                     }
                 }
@@ -418,7 +434,7 @@ attn_combine_kernel(T* __restrict__ out, float* __restrict__ row_max, float* __r
 
 // ------------------------------------------------------------------------------------------------ backward, destination sweep
 // Also the alpha writer of the forward (ALPHA_ONLY: alpha[e,h] from the saved statistics, nothing else).
-template <typename T, typename I, int G, int VPL, int MODE, bool ALPHA_ONLY, bool STAGED = false>
+template <typename T, typename I, int G, int VPL, int MODE, bool ALPHA_ONLY, int VAR = 0>      // VAR: see attn_fwd_kernel
 __global__ void __launch_bounds__(kAttnT)
 attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArgs a, const float* __restrict__ row_max,
                     const float* __restrict__ row_den, const T* __restrict__ out, const T* __restrict__ grad_out,
@@ -427,6 +443,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
     constexpr int EPV = ElemTraits<T>::kPerVec;
     constexpr int S = 32 / G;
     constexpr int UNR = VPL == 1 ? 4 : 2;
+    constexpr bool STAGED = VAR == 1, EDGE = VAR == 2 && MODE != ATTN_GAT;
     const int lane = threadIdx.x & 31;
     const int lig = lane & (G - 1);
     const int sub = lane / G;
@@ -481,24 +498,30 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
         }
 
         // one edge of this lane group: vbv / kbv = the gathered value (/ key) vectors, scv = GAT's a_src(+a_edge) scalars
-        auto process = [&](int64_t e, bool evu, const Vec16* vbv, const Vec16* kbv, const float* scv) {
-            float f[VPL][EPV], kf[VPL][EPV], l[VPL], dot[VPL];
+        // ebv (EDGE): the edge's feature vectors -- GATv2: z = x_l[j] + x_r[i] + e; DOT: key_j + e and value_j + e
+        auto process = [&](int64_t e, bool evu, const Vec16* vbv, const Vec16* kbv, const float* scv, const Vec16* ebv) {
+            float f[VPL][EPV], kf[VPL][EPV], ef[VPL][EPV], l[VPL], dot[VPL];
 #pragma unroll
             for (int k = 0; k < VPL; ++k) {
                 l[k] = dot[k] = 0.0f;
 #pragma unroll
-                for (int i = 0; i < EPV; ++i) f[k][i] = kf[k][i] = 0.0f;
+                for (int i = 0; i < EPV; ++i) f[k][i] = kf[k][i] = ef[k][i] = 0.0f;
                 if (evu && valid[k]) {
                     if (!ALPHA_ONLY || MODE == ATTN_GATV2) ElemTraits<T>::unpack(vbv[k], f[k]);
+                    if (EDGE) ElemTraits<T>::unpack(ebv[k], ef[k]);
                     if (MODE == ATTN_GAT) l[k] = scv[k] + sd[k];                         // pre-activation
                     if (MODE == ATTN_GATV2) {
 #pragma unroll
-                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i], a.slope), l[k]);
+                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(av[k][i], leaky_f(f[k][i] + qv[k][i] + ef[k][i], a.slope), l[k]);
                     }
                     if (MODE == ATTN_DOT) {
                         ElemTraits<T>::unpack(kbv[k], kf[k]);
 #pragma unroll
-                        for (int i = 0; i < EPV; ++i) l[k] = fmaf(qv[k][i], kf[k][i], l[k]);
+                        for (int i = 0; i < EPV; ++i) {
+                            kf[k][i] += ef[k][i];                                        // key_j + e
+                            f[k][i] += ef[k][i];                                         // value_j + e
+                            l[k] = fmaf(qv[k][i], kf[k][i], l[k]);
+                        }
                     }
                     if (!ALPHA_ONLY) {
 #pragma unroll
@@ -532,19 +555,26 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
                     gs *= (l[k] > 0.0f ? 1.0f : a.slope);
                     if (first) gsd[k] += gs;
                 }
+                float ge[EPV];                                           // EDGE: gradient of the edge's feature vector
                 if (MODE == ATTN_GATV2) {
 #pragma unroll
                     for (int i = 0; i < EPV; ++i) {
-                        const float z = f[k][i] + qv[k][i];
-                        gq[k][i] = fmaf(gs * av[k][i], (z > 0.0f ? 1.0f : a.slope), gq[k][i]);
+                        const float z = f[k][i] + qv[k][i] + ef[k][i];
+                        ge[i] = gs * av[k][i] * (z > 0.0f ? 1.0f : a.slope);
+                        gq[k][i] += ge[i];
                         gatt[k][i] = fmaf(gs, leaky_f(z, a.slope), gatt[k][i]);
                     }
                 }
                 if (MODE == ATTN_DOT) {
                     gs *= a.scale;
 #pragma unroll
-                    for (int i = 0; i < EPV; ++i) gq[k][i] = fmaf(gs, kf[k][i], gq[k][i]);
+                    for (int i = 0; i < EPV; ++i) {
+                        gq[k][i] = fmaf(gs, kf[k][i], gq[k][i]);
+                        ge[i] = fmaf(alpha * keep, gv[k][i], gs * qv[k][i]);      // through the value and through the key
+                    }
                 }
+                if (EDGE)
+                    stg_stream16(a.grad_ee + static_cast<size_t>(e) * row_bytes + static_cast<size_t>(lig + k * G) * 16, ElemTraits<T>::pack(ge));
                 if (first) *reinterpret_cast<float2*>(pair + (e * a.heads + head[k]) * 2) = make_float2(alpha * keep, gs);
             }
         };
@@ -608,7 +638,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
                             if (a.s_edge) sc0 += __ldg(a.s_edge + e * a.heads + head[0]);
                         }
                     }
-                    process(e, evu, &v0, &k0, &sc0);
+                    process(e, evu, &v0, &k0, &sc0, nullptr);
                 }
             }
             cp_async_wait<0>();
@@ -619,7 +649,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
             const int nb = static_cast<int>(end - b0 < 32 ? end - b0 : 32);
             c_next = (b0 + 32 + lane < end) ? ldg_idx(col + b0 + 32 + lane) : I(0);
             for (int j0 = 0; j0 < nb; j0 += S * UNR) {
-                Vec16 vb[UNR][VPL], kb[UNR][VPL];
+                Vec16 vb[UNR][VPL], kb[UNR][VPL], eb[UNR][VPL];
                 float sc[UNR][VPL];
                 bool ev[UNR];
 #pragma unroll
@@ -636,6 +666,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
                             if (!valid[k]) continue;
                             const size_t off = static_cast<size_t>(lig + k * G) * 16;
                             if (!ALPHA_ONLY || MODE == ATTN_GATV2) vb[u][k] = ldg_row16(a.v + static_cast<size_t>(c) * a.v_stride + off);
+                            if (EDGE) eb[u][k] = ldg_stream16(a.ee + static_cast<size_t>(e) * row_bytes + off);
                             if (MODE == ATTN_DOT) kb[u][k] = ldg_row16(a.k + static_cast<size_t>(c) * a.k_stride + off);
                             if (MODE == ATTN_GAT) {
                                 sc[u][k] = __ldg(a.s_src + c * a.heads + head[k]);
@@ -645,7 +676,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) process(b0 + j0 + u * S + sub, ev[u], vb[u], kb[u], sc[u]);
+                for (int u = 0; u < UNR; ++u) process(b0 + j0 + u * S + sub, ev[u], vb[u], kb[u], sc[u], eb[u]);
             }
         }
         }   // !STAGED
@@ -713,7 +744,7 @@ attn_bwd_dst_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, Att
 }
 
 // ------------------------------------------------------------------------------------------------ backward, source sweep
-template <typename T, typename I, int G, int VPL, int MODE, bool STAGED = false, int BT = kAttnT>
+template <typename T, typename I, int G, int VPL, int MODE, int VAR = 0, int BT = kAttnT>      // VAR: see attn_fwd_kernel
 __global__ void __launch_bounds__(BT)          // no register cap: capping at 64 serialised the row loads (8.0 -> 14.8 ms)
 attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t, const I* __restrict__ t2csr, AttnArgs a,
                     const T* __restrict__ grad_out, const float* __restrict__ pair, T* __restrict__ grad_v,
@@ -721,6 +752,7 @@ attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t,
     constexpr int EPV = ElemTraits<T>::kPerVec;
     constexpr int S = 32 / G;
     constexpr int UNR = VPL == 1 ? 4 : 2;
+    constexpr bool STAGED = VAR == 1, EDGE = VAR == 2 && MODE == ATTN_GATV2;   // (DOT: no edge term on this side)
     const int lane = threadIdx.x & 31;
     const int lig = lane & (G - 1);
     const int sub = lane / G;
@@ -762,7 +794,12 @@ attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t,
             if (MODE != ATTN_GAT) {
                 float qf[EPV];
                 ElemTraits<T>::unpack(qv_[k], qf);
-                if (MODE == ATTN_GATV2) {
+                if (MODE == ATTN_GATV2 && EDGE) {
+                    // qv_ holds the edge's grad_ee row (= gs att leaky'(x_l + x_r + e), written by the destination sweep):
+                    // the same quantity flows into x_l[j]
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) accv[k][i] += qf[i];
+                } else if (MODE == ATTN_GATV2) {
 #pragma unroll
                     for (int i = 0; i < EPV; ++i) accv[k][i] = fmaf(gs * av[k][i], ((xl[k][i] + qf[i]) > 0.0f ? 1.0f : a.slope), accv[k][i]);
                 } else {
@@ -866,7 +903,8 @@ attn_bwd_src_kernel(const I* __restrict__ rowptr_t, const I* __restrict__ col_t,
                         if (!valid[k]) continue;
                         const size_t off = static_cast<size_t>(lig + k * G) * 16;
                         gbuf[u][k] = ldg_row16(gb + static_cast<size_t>(d) * row_bytes + off);
-                        if (MODE != ATTN_GAT) qb[u][k] = ldg_row16(a.q + static_cast<size_t>(d) * a.q_stride + off);
+                        if (EDGE) qb[u][k] = ldg_row16(a.grad_ee + static_cast<size_t>(p) * row_bytes + off);
+                        else if (MODE != ATTN_GAT) qb[u][k] = ldg_row16(a.q + static_cast<size_t>(d) * a.q_stride + off);
                         pr[u][k] = __ldg(reinterpret_cast<const float2*>(pair) + p * a.heads + head[k]);
                     }
                 }
@@ -1004,7 +1042,17 @@ int attn_forward_typed(const void* rowptr_, const void* col_, AttnArgs a, void* 
 #define ATTN_FWD_STAGED1(G_) attn_fwd_kernel<T, I, G_, 1, MODE, true, 32><<<static_cast<unsigned>(items), 32, stage_bytes / (kAttnT / 32), s>>>(rowptr, col, a, out, row_max, row_den, n_rows, plan, part_ms)
     // lane-private cp.async slots: 2 iterations x 4 edges x (value (+ key) vector + a_src scalar) per thread
     const size_t stage_bytes = static_cast<size_t>(2) * 4 * kAttnT * ((MODE == ATTN_DOT ? 2 : 1) * 16 + 4);
-    if (get_option_attn_staged() == 2 && n_vec > 4 && n_vec <= 32) {          // one-warp CTAs
+    bool edge_done = false;
+    if constexpr (MODE != ATTN_GAT) {
+        if (a.ee) {                                                            // per-edge feature rows: register form
+#define ATTN_FWD_EDGE(G_, V_) attn_fwd_kernel<T, I, G_, V_, MODE, 2><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, out, row_max, row_den, n_rows, plan, part_ms)
+            ATTN_BY_SHAPE(ATTN_FWD_EDGE);
+#undef ATTN_FWD_EDGE
+            edge_done = true;
+        }
+    }
+    if (edge_done) {
+    } else if (get_option_attn_staged() == 2 && n_vec > 4 && n_vec <= 32) {          // one-warp CTAs
         if (n_vec <= 8) ATTN_FWD_STAGED1(8);
         else if (n_vec <= 16) ATTN_FWD_STAGED1(16);
         else ATTN_FWD_STAGED1(32);
@@ -1028,7 +1076,16 @@ int attn_forward_typed(const void* rowptr_, const void* col_, AttnArgs a, void* 
         LongRowPlan np = plan;
         np.partials = nullptr;
 #define ATTN_ALPHA(G_, V_) attn_bwd_dst_kernel<T, I, G_, V_, MODE, true><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, row_max, row_den, nullptr, nullptr, nullptr, alpha_out, nullptr, nullptr, nullptr, n_rows, np)
-        ATTN_BY_SHAPE(ATTN_ALPHA);
+#define ATTN_ALPHA_EDGE(G_, V_) attn_bwd_dst_kernel<T, I, G_, V_, MODE, true, 2><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, row_max, row_den, nullptr, nullptr, nullptr, alpha_out, nullptr, nullptr, nullptr, n_rows, np)
+        bool alpha_done = false;
+        if constexpr (MODE != ATTN_GAT) {
+            if (a.ee) {
+                ATTN_BY_SHAPE(ATTN_ALPHA_EDGE);
+                alpha_done = true;
+            }
+        }
+        if (!alpha_done) ATTN_BY_SHAPE(ATTN_ALPHA);
+#undef ATTN_ALPHA_EDGE
 #undef ATTN_ALPHA
         B200MP_LAUNCH_CHECK();
     }
@@ -1053,7 +1110,17 @@ int attn_backward_typed(const void* rowptr_, const void* col_, const void* rowpt
 #define ATTN_DST(G_, V_) attn_bwd_dst_kernel<T, I, G_, V_, MODE, false><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, row_max, row_den, static_cast<const T*>(out), static_cast<const T*>(grad_out), pair, nullptr, static_cast<T*>(grad_q), grad_s_dst, gatt_part, n_rows, plan)
 #define ATTN_DST_STAGED(G_) attn_bwd_dst_kernel<T, I, G_, 1, MODE, false, true><<<blocks, kAttnT, dst_stage, s>>>(rowptr, col, a, row_max, row_den, static_cast<const T*>(out), static_cast<const T*>(grad_out), pair, nullptr, static_cast<T*>(grad_q), grad_s_dst, gatt_part, n_rows, plan)
         const size_t dst_stage = static_cast<size_t>(2) * 4 * kAttnT * ((MODE == ATTN_DOT ? 2 : 1) * 16 + 4);
-        if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
+        bool edge_done = false;
+        if constexpr (MODE != ATTN_GAT) {
+            if (a.ee) {
+#define ATTN_DST_EDGE(G_, V_) attn_bwd_dst_kernel<T, I, G_, V_, MODE, false, 2><<<blocks, kAttnT, 0, s>>>(rowptr, col, a, row_max, row_den, static_cast<const T*>(out), static_cast<const T*>(grad_out), pair, nullptr, static_cast<T*>(grad_q), grad_s_dst, gatt_part, n_rows, plan)
+                ATTN_BY_SHAPE(ATTN_DST_EDGE);
+#undef ATTN_DST_EDGE
+                edge_done = true;
+            }
+        }
+        if (edge_done) {
+        } else if (get_option_attn_staged() && n_vec > 4 && n_vec <= 32) {
             if (n_vec <= 8) ATTN_DST_STAGED(8);
             else if (n_vec <= 16) ATTN_DST_STAGED(16);
             else ATTN_DST_STAGED(32);
@@ -1084,7 +1151,17 @@ int attn_backward_typed(const void* rowptr_, const void* col_, const void* rowpt
 #define ATTN_SRC_STAGED(G_) attn_bwd_src_kernel<T, I, G_, 1, MODE, true><<<blocks, kAttnT, src_stage, s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
 #define ATTN_SRC_STAGED1(G_) attn_bwd_src_kernel<T, I, G_, 1, MODE, true, 32><<<static_cast<unsigned>(items), 32, src_stage / (kAttnT / 32), s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
         const size_t src_stage = static_cast<size_t>(2) * 4 * kAttnT * ((MODE == ATTN_GAT ? 1 : 2) * 16 + 8);
-        if (get_option_attn_staged() == 2 && n_vec > 4 && n_vec <= 32) {
+        bool edge_done = false;
+        if constexpr (MODE == ATTN_GATV2) {
+            if (a.ee) {                                 // x_l's gradient takes the edges' grad_ee rows instead of recomputing them
+#define ATTN_SRC_EDGE(G_, V_) attn_bwd_src_kernel<T, I, G_, V_, MODE, 2><<<blocks, kAttnT, 0, s>>>(static_cast<const I*>(rowptr_t_), static_cast<const I*>(col_t_), static_cast<const I*>(t2csr_), a, static_cast<const T*>(grad_out), pair, static_cast<T*>(grad_v), static_cast<T*>(grad_k), grad_s_src, n_src, plan_t)
+                ATTN_BY_SHAPE(ATTN_SRC_EDGE);
+#undef ATTN_SRC_EDGE
+                edge_done = true;
+            }
+        }
+        if (edge_done) {
+        } else if (get_option_attn_staged() == 2 && n_vec > 4 && n_vec <= 32) {
             if (n_vec <= 8) ATTN_SRC_STAGED1(8);
             else if (n_vec <= 16) ATTN_SRC_STAGED1(16);
             else ATTN_SRC_STAGED1(32);
@@ -1118,7 +1195,8 @@ namespace {
 
 int fill_args(AttnArgs& a, int mode, const void* v, const void* k, const void* q, const float* s_src, const float* s_dst,
               const float* att, const float* s_edge, int64_t v_stride, int64_t k_stride, int64_t q_stride, int64_t heads,
-              int64_t chan, float slope, float scale, int val_dtype, float dropout_p, unsigned long long dropout_seed) {
+              int64_t chan, float slope, float scale, int val_dtype, float dropout_p, unsigned long long dropout_seed,
+              const void* edge_feat, void* grad_edge_feat) {
     const size_t es = val_dtype == B200MP_BF16 ? 2 : 4;
     if (!(dropout_p >= 0.0f && dropout_p < 1.0f)) return 1;
     a.drop_thresh = dropout_p > 0.0f ? static_cast<uint32_t>(fmin(4294967295.0, ceil(static_cast<double>(dropout_p) * 4294967296.0))) : 0u;
@@ -1132,6 +1210,9 @@ int fill_args(AttnArgs& a, int mode, const void* v, const void* k, const void* q
     a.s_dst = s_dst;
     a.att = att;
     a.s_edge = s_edge;
+    a.ee = static_cast<const char*>(edge_feat);
+    a.grad_ee = static_cast<char*>(grad_edge_feat);
+    if (a.ee && (mode == ATTN_GAT || !aligned16(a.ee) || !aligned16(a.grad_ee))) return 1;
     a.v_stride = v_stride > 0 ? static_cast<size_t>(v_stride) * es : hc_bytes;
     a.k_stride = k_stride > 0 ? static_cast<size_t>(k_stride) * es : hc_bytes;
     a.q_stride = q_stride > 0 ? static_cast<size_t>(q_stride) * es : hc_bytes;
@@ -1190,7 +1271,7 @@ extern "C" int b200mp_attn_csr_forward(int mode, const void* rowptr, const void*
                                        void* out, float* row_max, float* row_den, float* alpha_out, int64_t n_rows,
                                        int64_t n_edges, int64_t heads, int64_t chan, float slope, float scale,
                                        const int64_t* long_rows, const int64_t* chunk_ptr, int64_t n_long_rows,
-                                       int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, float dropout_p, unsigned long long dropout_seed, int idx_dtype,
+                                       int64_t n_chunks, int64_t chunk, float* part_acc, float* part_ms, float dropout_p, unsigned long long dropout_seed, const void* edge_feat, int idx_dtype,
                                        int val_dtype, void* stream) {
     B200MP_CHECK_ARG(mode >= ATTN_GAT && mode <= ATTN_DOT);
     B200MP_CHECK_ARG(n_rows >= 0 && n_edges >= 0 && heads > 0 && chan > 0);
@@ -1198,7 +1279,7 @@ extern "C" int b200mp_attn_csr_forward(int mode, const void* rowptr, const void*
     B200MP_CHECK_ARG(rowptr && out && row_max && row_den && (n_edges == 0 || (col && v)));
     B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && part_acc && part_ms && chunk > 0));
     AttnArgs a;
-    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype, dropout_p, dropout_seed)) {
+    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype, dropout_p, dropout_seed, edge_feat, nullptr)) {
         set_error("attn forward: operands missing for mode %d (or dropout_p outside [0, 1))", mode);
         return B200MP_ERR_INVALID_ARG;
     }
@@ -1232,7 +1313,7 @@ extern "C" int b200mp_attn_csr_backward(int mode, const void* rowptr, const void
                                         int64_t chan, float slope, float scale, const int64_t* long_rows,
                                         const int64_t* chunk_ptr, int64_t n_long_rows, int64_t n_chunks, int64_t chunk,
                                         float* partials, const int64_t* long_rows_t, const int64_t* chunk_ptr_t,
-                                        int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, float dropout_p, unsigned long long dropout_seed, int idx_dtype,
+                                        int64_t n_long_rows_t, int64_t n_chunks_t, float* partials_t, float dropout_p, unsigned long long dropout_seed, const void* edge_feat, void* grad_edge_feat, int idx_dtype,
                                         int val_dtype, void* stream) {
     B200MP_CHECK_ARG(mode >= ATTN_GAT && mode <= ATTN_DOT);
     B200MP_CHECK_ARG(n_rows >= 0 && n_src >= 0 && n_edges >= 0 && heads > 0 && chan > 0);
@@ -1245,7 +1326,7 @@ extern "C" int b200mp_attn_csr_backward(int mode, const void* rowptr, const void
     B200MP_CHECK_ARG(n_long_rows == 0 || (long_rows && chunk_ptr && partials && chunk > 0));
     B200MP_CHECK_ARG(n_long_rows_t == 0 || (long_rows_t && chunk_ptr_t && partials_t && chunk > 0));
     AttnArgs a;
-    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype, dropout_p, dropout_seed)) {
+    if (fill_args(a, mode, v, k, q, s_src, s_dst, att, s_edge, v_stride, k_stride, q_stride, heads, chan, slope, scale, val_dtype, dropout_p, dropout_seed, edge_feat, grad_edge_feat)) {
         set_error("attn backward: operands missing for mode %d (or dropout_p outside [0, 1))", mode);
         return B200MP_ERR_INVALID_ARG;
     }

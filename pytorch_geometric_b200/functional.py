@@ -217,7 +217,8 @@ class _AttnFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mode: str, graph: CSRGraph, heads: int, chan: int, slope: float, scale: float, want_alpha: bool,
                 v: Tensor, k: Optional[Tensor], q: Optional[Tensor], s_src: Optional[Tensor], s_dst: Optional[Tensor],
-                att: Optional[Tensor], s_edge: Optional[Tensor], kv: Optional[Tensor], dropout: tuple = (0.0, 0)):
+                att: Optional[Tensor], s_edge: Optional[Tensor], kv: Optional[Tensor], dropout: tuple = (0.0, 0),
+                e_feat: Optional[Tensor] = None):
         hc = heads * chan
         if kv is not None:                                   # keys | values as the two halves of one [N, 2HC] product
             k, v = kv[:, :hc], kv[:, hc:]
@@ -226,15 +227,17 @@ class _AttnFused(torch.autograd.Function):
         s_edge_csr = None if s_edge is None else graph.to_csr_order_rows(f32(s_edge))
         if q is not None and q.stride(1) != 1:
             q = q.contiguous()
+        ref = kv if kv is not None else v
+        e_csr = None if e_feat is None else graph.to_csr_order_rows(e_feat.detach().to(ref.dtype).contiguous())
         out, row_max, row_den, alpha = ops.attn_forward(mode, graph.rowptr, graph.col, v, heads, chan, k=k, q=q, s_src=s_src32,
                                                         s_dst=s_dst32, att=att32, s_edge=s_edge_csr, slope=slope, scale=scale,
                                                         want_alpha=want_alpha, plan=graph.plan, dropout_p=dropout[0],
-                                                        dropout_seed=dropout[1])
+                                                        dropout_seed=dropout[1], edge_feat=e_csr)
         ctx.mode, ctx.graph, ctx.dims, ctx.fused_kv = mode, graph, (heads, chan, slope, scale), kv is not None
         ctx.dropout = dropout
-        ctx.dt = tuple(None if t is None else t.dtype for t in (s_src, s_dst, att, s_edge))
+        ctx.dt = tuple(None if t is None else t.dtype for t in (s_src, s_dst, att, s_edge, e_feat))
         ctx.save_for_backward(kv if kv is not None else v, None if kv is not None else k, q, s_src32, s_dst32, att32, s_edge_csr,
-                              row_max, row_den, out)
+                              row_max, row_den, out, e_csr)
         if alpha is None:
             alpha = out.new_empty(0)
         ctx.mark_non_differentiable(alpha)
@@ -242,7 +245,7 @@ class _AttnFused(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out: Tensor, _grad_alpha):
-        v, k, q, s_src, s_dst, att, s_edge, row_max, row_den, out = ctx.saved_tensors
+        v, k, q, s_src, s_dst, att, s_edge, row_max, row_den, out, e_csr = ctx.saved_tensors
         graph = ctx.graph
         heads, chan, slope, scale = ctx.dims
         hc = heads * chan
@@ -256,15 +259,18 @@ class _AttnFused(torch.autograd.Function):
         r = ops.attn_backward(ctx.mode, graph.rowptr, graph.col, graph.rowptr_t, graph.col_t, graph.t2csr, v, heads, chan,
                               row_max, row_den, out, grad_out, k=k, q=q, s_src=s_src, s_dst=s_dst, att=att, s_edge=s_edge,
                               slope=slope, scale=scale, plan=graph.plan, plan_t=graph.plan_t, grad_v=grad_v, grad_k=grad_k,
-                              dropout_p=ctx.dropout[0], dropout_seed=ctx.dropout[1])
+                              dropout_p=ctx.dropout[0], dropout_seed=ctx.dropout[1], edge_feat=e_csr)
         cast = lambda t, d: None if (t is None or d is None) else t.to(d)       # noqa: E731
         g_edge = None
         if s_edge is not None:
             g_edge = cast(graph.from_csr_order_rows(r["grad_s_edge"].contiguous()), ctx.dt[3])
         g_att = None if r["grad_att"] is None else cast(r["grad_att"], ctx.dt[2])
+        g_ef = None
+        if e_csr is not None and ctx.needs_input_grad[16]:
+            g_ef = cast(graph.from_csr_order_rows(r["grad_edge_feat"]), ctx.dt[4])
         return (None, None, None, None, None, None, None,
                 None if ctx.fused_kv else r["grad_v"], None if ctx.fused_kv else r["grad_k"], r["grad_q"],
-                cast(r["grad_s_src"], ctx.dt[0]), cast(r["grad_s_dst"], ctx.dt[1]), g_att, g_edge, grad_kv, None)
+                cast(r["grad_s_src"], ctx.dt[0]), cast(r["grad_s_dst"], ctx.dt[1]), g_att, g_edge, grad_kv, None, g_ef)
 
 
 def _vector_shape(heads: int, chan: int, dtype: torch.dtype):
@@ -286,10 +292,12 @@ def attention(mode: str, graph: CSRGraph, heads: int, chan: int, *, v: Optional[
               q: Optional[Tensor] = None, kv: Optional[Tensor] = None, s_src: Optional[Tensor] = None,
               s_dst: Optional[Tensor] = None, att: Optional[Tensor] = None, s_edge: Optional[Tensor] = None,
               negative_slope: float = 0.2, scale: float = 1.0, return_alpha: bool = False, dropout_p: float = 0.0,
-              dropout_seed: Optional[int] = None):
+              dropout_seed: Optional[int] = None, e_feat: Optional[Tensor] = None):
     """out[i,h,:] = sum_e softmax_i(score_e,h) v[j,h,:] for mode in {"gat", "gatv2", "dot"} (see csrc/attention.cu).
     dropout_p > 0: attention dropout (F.dropout on the normalised coefficients, gat_conv.py:404) inside the sweep; the
     seed is drawn from torch's CPU generator (reproducible under torch.manual_seed, no device sync) unless given.
+    e_feat [E, H*C] (caller's edge order; "gatv2" and "dot"): lin_edge(edge_attr) of `edge_dim` layers -- added inside
+    GATv2's leaky_relu (gatv2_conv.py:358-360) / to the key and the value of the dot mode (transformer_conv.py:258-272).
     All feature operands are [n, H*C]; `kv` = [n_src, 2*H*C] (keys | values from one fused product) instead of k, v;
     s_edge [E, H] in the caller's edge order.  Returns out (and alpha [E, H] in CSR order).
 
@@ -308,7 +316,7 @@ def attention(mode: str, graph: CSRGraph, heads: int, chan: int, *, v: Optional[
     drop = (float(dropout_p), int(dropout_seed or 0))
     if chan_p == chan and hpg == heads and ops.attn_supported(heads, chan, dtype):
         out, alpha = _AttnFused.apply(mode, graph, heads, chan, float(negative_slope), float(scale), return_alpha, v, k, q,
-                                      s_src, s_dst, att if att is None else att.reshape(-1), s_edge, kv, drop)
+                                      s_src, s_dst, att if att is None else att.reshape(-1), s_edge, kv, drop, e_feat)
         return (out, alpha) if return_alpha else out
     if kv is not None:
         k, v = kv[:, :heads * chan], kv[:, heads * chan:]
@@ -330,7 +338,8 @@ def attention(mode: str, graph: CSRGraph, heads: int, chan: int, *, v: Optional[
         o, al = _AttnFused.apply(mode, graph, h1 - h0, chan_p, float(negative_slope), float(scale), return_alpha,
                                  group(v, h0, h1, True), group(k, h0, h1, True), group(q, h0, h1, True),
                                  group(s_src, h0, h1, False), group(s_dst, h0, h1, False), a_g, group(s_edge, h0, h1, False),
-                                 None, (drop[0], drop[1] + 0x51ED27 * h0))          # a different stream per head group
+                                 None, (drop[0], drop[1] + 0x51ED27 * h0),          # a different stream per head group
+                                 group(e_feat, h0, h1, True))
         outs.append(o.view(o.size(0), h1 - h0, chan_p)[:, :, :chan])
         alphas.append(al)
     out = torch.cat(outs, dim=1).reshape(outs[0].size(0), heads * chan)

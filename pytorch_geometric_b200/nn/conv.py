@@ -260,10 +260,11 @@ def gat_conv(xh_src: Tensor, xh_dst: Optional[Tensor], graph: CSRGraph, att_src:
 
 def gatv2_conv(x_l: Tensor, x_r: Tensor, graph: CSRGraph, att: Tensor, H: int, C: int, negative_slope: float = 0.2,
                concat: bool = True, res: Optional[Tensor] = None, bias: Optional[Tensor] = None, return_alpha: bool = False,
-               dropout_p: float = 0.0):
-    """GATv2Conv after lin_l / lin_r (gatv2_conv.py:300-331, 356-378): x_l [n_src, H*C], x_r [n_dst, H*C]."""
+               dropout_p: float = 0.0, e_feat: Optional[Tensor] = None):
+    """GATv2Conv after lin_l / lin_r (gatv2_conv.py:300-331, 356-378): x_l [n_src, H*C], x_r [n_dst, H*C];
+    e_feat [E, H*C] = lin_edge(edge_attr) aligned with the edges the graph was built from (edge_dim)."""
     r = Fn.attention("gatv2", graph, H, C, v=x_l, q=x_r, att=att.reshape(-1), negative_slope=negative_slope,
-                     return_alpha=return_alpha, dropout_p=dropout_p)
+                     return_alpha=return_alpha, dropout_p=dropout_p, e_feat=e_feat)
     out, alpha = r if return_alpha else (r, None)
     out = _finish_heads(out, H, C, concat, res, bias)
     return (out, alpha) if return_alpha else out
@@ -271,11 +272,11 @@ def gatv2_conv(x_l: Tensor, x_r: Tensor, graph: CSRGraph, att: Tensor, H: int, C
 
 def transformer_conv(query: Tensor, kv: Tensor, graph: CSRGraph, H: int, C: int, concat: bool = True,
                      x_skip: Optional[Tensor] = None, w_beta: Optional[Tensor] = None, return_alpha: bool = False,
-                     dropout_p: float = 0.0):
+                     dropout_p: float = 0.0, e_feat: Optional[Tensor] = None):
     """TransformerConv after its linear maps (transformer_conv.py:222-275): query [n_dst, H*C], kv [n_src, 2*H*C]
     (keys | values from ONE product with the concatenated lin_key / lin_value weights); x_skip = lin_skip(x_dst)."""
     r = Fn.attention("dot", graph, H, C, q=query, kv=kv, scale=1.0 / math.sqrt(C), return_alpha=return_alpha,
-                     dropout_p=dropout_p)
+                     dropout_p=dropout_p, e_feat=e_feat)            # e_feat = lin_edge(edge_attr): added to key_j and value_j
     out, alpha = r if return_alpha else (r, None)
     if not concat:
         out = out.view(-1, H, C).mean(dim=1)
@@ -622,17 +623,16 @@ class GATConv(torch.nn.Module):
 
 
 class GATv2Conv(torch.nn.Module):
-    """Mirror of torch_geometric.nn.GATv2Conv (nn/conv/gatv2_conv.py:24-385) without edge_dim: the score
-    att . leaky_relu(x_l[j] + x_r[i]), the edge softmax and the aggregation are ONE sweep (csrc/attention.cu)."""
+    """Mirror of torch_geometric.nn.GATv2Conv (nn/conv/gatv2_conv.py:24-385) incl. `edge_dim`: the score
+    att . leaky_relu(x_l[j] + x_r[i] (+ lin_edge(e_ij))), the edge softmax and the aggregation are ONE sweep (csrc/attention.cu)."""
 
     def __init__(self, in_channels, out_channels: int, heads: int = 1, concat: bool = True, negative_slope: float = 0.2,
                  dropout: float = 0.0, add_self_loops: bool = True, edge_dim: Optional[int] = None, fill_value="mean",
                  bias: bool = True, residual: bool = False, share_weights: bool = False, **kwargs):
         super().__init__()
-        if edge_dim is not None:
-            raise NotImplementedError("edge_dim is not on the fused GATv2 path")
         self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
         self.negative_slope, self.dropout, self.add_self_loops = negative_slope, dropout, add_self_loops
+        self.edge_dim, self.fill_value = edge_dim, fill_value
         self.residual, self.share_weights = residual, share_weights
         self.flow = kwargs.get("flow", "source_to_target")
         ic = (in_channels, in_channels) if isinstance(in_channels, int) else in_channels
@@ -640,14 +640,13 @@ class GATv2Conv(torch.nn.Module):
         self.lin_r = self.lin_l if share_weights else _Lin(ic[1], heads * out_channels, bias=bias)
         self.att = torch.nn.Parameter(torch.empty(1, heads, out_channels))
         glorot_(self.att)
+        self.lin_edge = _Lin(edge_dim, heads * out_channels, bias=False) if edge_dim is not None else None
         total = heads * out_channels if concat else out_channels
         self.res = _Lin(ic[1], total, bias=False) if residual else None
         self.bias = torch.nn.Parameter(torch.zeros(total)) if bias else None
 
     def forward(self, x, edge_index: Adj, edge_attr=None, return_attention_weights: Optional[bool] = None):
         drop = float(self.dropout) if self.training else 0.0        # attention dropout runs inside the sweep
-        if edge_attr is not None:
-            raise NotImplementedError("edge_attr is not on the fused GATv2 path")
         H, C = self.heads, self.out_channels
         if isinstance(x, Tensor):
             res = self.res(x) if self.res is not None else None
@@ -658,8 +657,16 @@ class GATv2Conv(torch.nn.Module):
             x_l = self.lin_l(x[0])
             x_r = self.lin_r(x[1])
         graph = _attention_graph(edge_index, x_l.size(0), x_r.size(0), self.add_self_loops, self.flow)
+        e_feat = None
+        if edge_attr is not None and self.lin_edge is not None:         # gatv2_conv.py:318-325, 358-360
+            if isinstance(edge_index, CSRGraph):
+                raise ValueError("edge_attr needs the [2, E] edge_index it is aligned with")
+            ea = edge_attr
+            if self.add_self_loops:
+                ea = edge_attr_with_loops(edge_index, edge_attr, min(x_l.size(0), x_r.size(0)), self.fill_value, self.flow)
+            e_feat = self.lin_edge(ea.view(-1, 1) if ea.dim() == 1 else ea)
         want = return_attention_weights is not None
-        r = gatv2_conv(x_l, x_r, graph, self.att, H, C, self.negative_slope, self.concat, res, self.bias, want, drop)
+        r = gatv2_conv(x_l, x_r, graph, self.att, H, C, self.negative_slope, self.concat, res, self.bias, want, drop, e_feat)
         if want:
             out, alpha = r
             return out, (torch.stack([graph.col.long(), graph.dst_csr.long()]), alpha)
@@ -670,15 +677,14 @@ class GATv2Conv(torch.nn.Module):
 
 
 class TransformerConv(torch.nn.Module):
-    """Mirror of torch_geometric.nn.TransformerConv (nn/conv/transformer_conv.py:17-285) without edge_dim:
-    q.k / sqrt(C) scores, edge softmax and the value aggregation in ONE sweep; keys and values come from one GEMM
+    """Mirror of torch_geometric.nn.TransformerConv (nn/conv/transformer_conv.py:17-285) incl. `edge_dim` (lin_edge(e_ij) added
+    to the key and to the value): q.k / sqrt(C) scores, edge softmax and the value aggregation in ONE sweep; keys and values come from one GEMM
     with the concatenated lin_key / lin_value weights and are read as the two halves of one [N, 2HC] matrix."""
 
     def __init__(self, in_channels, out_channels: int, heads: int = 1, concat: bool = True, beta: bool = False,
                  dropout: float = 0.0, edge_dim: Optional[int] = None, bias: bool = True, root_weight: bool = True, **kwargs):
         super().__init__()
-        if edge_dim is not None:
-            raise NotImplementedError("edge_dim is not on the fused TransformerConv path")
+        self.edge_dim = edge_dim
         self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
         self.beta, self.root_weight, self.dropout = beta and root_weight, root_weight, dropout
         self.flow = kwargs.get("flow", "source_to_target")
@@ -687,16 +693,21 @@ class TransformerConv(torch.nn.Module):
         self.lin_key = _Lin(ic[0], hc, bias=bias)
         self.lin_query = _Lin(ic[1], hc, bias=bias)
         self.lin_value = _Lin(ic[0], hc, bias=bias)
+        self.lin_edge = _Lin(edge_dim, hc, bias=False) if edge_dim is not None else None
         total = hc if concat else out_channels
         self.lin_skip = _Lin(ic[1], total, bias=bias)
         self.lin_beta = _Lin(3 * total, 1, bias=False) if self.beta else None
 
     def forward(self, x, edge_index: Adj, edge_attr=None, return_attention_weights: Optional[bool] = None):
         drop = float(self.dropout) if self.training else 0.0        # attention dropout runs inside the sweep
-        if edge_attr is not None:
-            raise NotImplementedError("edge_attr is not on the fused TransformerConv path")
         H, C = self.heads, self.out_channels
         x = _pair(x)
+        e_feat = None
+        if self.lin_edge is not None:                                   # transformer_conv.py:258-261
+            assert edge_attr is not None
+            if isinstance(edge_index, CSRGraph):
+                raise ValueError("edge_attr needs the [2, E] edge_index it is aligned with")
+            e_feat = self.lin_edge(edge_attr.view(-1, 1) if edge_attr.dim() == 1 else edge_attr)
         query = self.lin_query(x[1])
         w_kv = torch.cat([self.lin_key.weight, self.lin_value.weight], dim=0)
         b_kv = None if self.lin_key.bias is None else torch.cat([self.lin_key.bias, self.lin_value.bias], dim=0)
@@ -704,7 +715,7 @@ class TransformerConv(torch.nn.Module):
         graph = _plain_graph(edge_index, x[0].size(0), x[1].size(0), self.flow)
         x_skip = self.lin_skip(x[1]) if self.root_weight else None
         want = isinstance(return_attention_weights, bool)
-        r = transformer_conv(query, kv, graph, H, C, self.concat, x_skip, _w(self.lin_beta), want, drop)
+        r = transformer_conv(query, kv, graph, H, C, self.concat, x_skip, _w(self.lin_beta), want, drop, e_feat)
         if want:
             out, alpha = r
             return out, (torch.stack([graph.col.long(), graph.dst_csr.long()]), alpha)

@@ -560,11 +560,17 @@ def _row_stride(t: Optional[Tensor], hc: int) -> int:
 def attn_forward(mode: str, rowptr: Tensor, col: Tensor, v: Tensor, heads: int, chan: int, *, k: Optional[Tensor] = None,
                  q: Optional[Tensor] = None, s_src: Optional[Tensor] = None, s_dst: Optional[Tensor] = None,
                  att: Optional[Tensor] = None, s_edge: Optional[Tensor] = None, slope: float = 0.2, scale: float = 1.0,
-                 want_alpha: bool = False, plan: Optional["LongRowPlan"] = None, dropout_p: float = 0.0, dropout_seed: int = 0):
+                 want_alpha: bool = False, plan: Optional["LongRowPlan"] = None, dropout_p: float = 0.0, dropout_seed: int = 0,
+                 edge_feat: Optional[Tensor] = None):
     """Fused edge-softmax attention + aggregation (b200mp_attn_csr_forward).  v / k: [n_src, H*C] (column slices of
     a wider matrix are fine), q: [n_rows, H*C].  Returns (out, row_max, row_den, alpha or None).
-    dropout_p / dropout_seed: attention dropout fused into the sweep (pass the same pair to attn_backward)."""
-    _cuda(rowptr, col, v, k, q, s_src, s_dst, att, s_edge)
+    dropout_p / dropout_seed: attention dropout fused into the sweep (pass the same pair to attn_backward).
+    edge_feat: [E, H*C] per-edge feature rows in CSR order (gatv2 / dot modes, `edge_dim` layers)."""
+    _cuda(rowptr, col, v, k, q, s_src, s_dst, att, s_edge, edge_feat)
+    if edge_feat is not None:
+        if mode == "gat" or edge_feat.shape != (col.numel(), heads * chan) or edge_feat.dtype != v.dtype:
+            raise ValueError("edge_feat must be [E, heads*chan] of the value dtype (gatv2 / dot modes)")
+        edge_feat = edge_feat.contiguous()
     it = _same_idx(rowptr, col)
     hc = heads * chan
     n_rows = rowptr.numel() - 1
@@ -578,18 +584,23 @@ def attn_forward(mode: str, rowptr: Tensor, col: Tensor, v: Tensor, heads: int, 
     _timed("attn_forward", launches, lib().b200mp_attn_csr_forward, ATTN_MODES[mode], _p(rowptr), _p(col), _p(v), _p(k), _p(q),
            _p(s_src), _p(s_dst), _p(att), _p(s_edge), _row_stride(v, hc), _row_stride(k, hc), _row_stride(q, hc), _p(out),
            _p(row_max), _p(row_den), _p(alpha), n_rows, col.numel(), heads, chan, float(slope), float(scale), *pargs,
-           _p(part_ms), float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, it, _vdt(v), _stream())
+           _p(part_ms), float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _p(edge_feat), it, _vdt(v), _stream())
     return out, row_max, row_den, alpha
 
 
 def attn_backward(mode: str, rowptr, col, rowptr_t, col_t, t2csr, v: Tensor, heads: int, chan: int, row_max, row_den, out,
                   grad_out, *, k=None, q=None, s_src=None, s_dst=None, att=None, s_edge=None, slope: float = 0.2,
                   scale: float = 1.0, plan=None, plan_t=None, grad_v: Optional[Tensor] = None,
-                  grad_k: Optional[Tensor] = None, dropout_p: float = 0.0, dropout_seed: int = 0):
+                  grad_k: Optional[Tensor] = None, dropout_p: float = 0.0, dropout_seed: int = 0,
+                  edge_feat: Optional[Tensor] = None):
     """Backward of attn_forward.  Returns a dict with grad_v, and per mode grad_k / grad_q / grad_s_src /
     grad_s_dst / grad_att / grad_s_edge.  grad_v / grad_k may be preallocated (column slices of one matrix)."""
-    _cuda(rowptr, col, rowptr_t, col_t, t2csr, v, grad_out)
+    _cuda(rowptr, col, rowptr_t, col_t, t2csr, v, grad_out, edge_feat)
     it = _same_idx(rowptr, col, rowptr_t, col_t, t2csr)
+    grad_ef = None
+    if edge_feat is not None:
+        edge_feat = edge_feat.contiguous()
+        grad_ef = torch.empty_like(edge_feat)
     m = ATTN_MODES[mode]
     hc = heads * chan
     dev = v.device
@@ -623,8 +634,10 @@ def attn_backward(mode: str, rowptr, col, rowptr_t, col_t, t2csr, v: Tensor, hea
            _p(s_edge), _row_stride(v, hc), _row_stride(k, hc), _row_stride(q, hc), _p(row_max), _p(row_den), _p(out),
            _p(grad_out), _p(pair), _p(grad_v), _p(grad_k), _p(grad_q), _p(gss), _p(gsd), _p(gatt), _p(gatt_part), n_rows,
            n_src, n_edges, heads, chan, float(slope), float(scale), pa[0], pa[1], pa[2], pa[3], pa[4], pa[5], pt[0],
-           pt[1], pt[2], pt[3], pt[5], float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, it, _vdt(v), _stream())
-    res = {"grad_v": grad_v, "grad_k": grad_k, "grad_q": grad_q, "grad_s_src": gss, "grad_s_dst": gsd, "grad_att": gatt}
+           pt[1], pt[2], pt[3], pt[5], float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _p(edge_feat), _p(grad_ef), it,
+           _vdt(v), _stream())
+    res = {"grad_v": grad_v, "grad_k": grad_k, "grad_q": grad_q, "grad_s_src": gss, "grad_s_dst": gsd, "grad_att": gatt,
+           "grad_edge_feat": grad_ef}
     if s_edge is not None:
         res["grad_s_edge"] = pair[:, :, 1]
     return res

@@ -208,7 +208,8 @@ class B200GATConv(tgnn.GATConv):
 class B200GATv2Conv(tgnn.GATv2Conv):
     def forward(self, x, edge_index, edge_attr=None, return_attention_weights=None):
         xs = _pair(x)
-        if (xs[0].dim() == 2 and xs[1] is not None and _attn_fast(self, xs[0], xs[1]) and edge_attr is None
+        if (xs[0].dim() == 2 and xs[1] is not None and _attn_fast(self, xs[0], xs[1], edge_attr)
+                and (edge_attr is None) == (self.lin_edge is None)
                 and return_attention_weights is None and isinstance(edge_index, Tensor) and edge_index.layout == torch.strided):
             H, Cc = self.heads, self.out_channels
             res = dense.linear(xs[1], self.res.weight) if self.res is not None else None
@@ -217,19 +218,25 @@ class B200GATv2Conv(tgnn.GATv2Conv):
                 x_r = x_l
             else:
                 x_r = dense.linear(xs[1], self.lin_r.weight, self.lin_r.bias)
-            g = cached_graph(_plain(edge_index), x_l.size(0), x_r.size(0), flow=self.flow,
+            ei = _plain(edge_index)
+            g = cached_graph(ei, x_l.size(0), x_r.size(0), flow=self.flow,
                              loops="gat" if self.add_self_loops else None, loop_nodes=min(x_l.size(0), x_r.size(0)))
+            e_feat = None
+            if edge_attr is not None:                                           # gatv2_conv.py:318-325, 358-360
+                ea = edge_attr if not self.add_self_loops else C.edge_attr_with_loops(
+                    ei, edge_attr, min(x_l.size(0), x_r.size(0)), self.fill_value, self.flow)
+                e_feat = dense.linear(ea.view(-1, 1) if ea.dim() == 1 else ea, self.lin_edge.weight)
             return C.gatv2_conv(x_l, x_r, g, self.att, H, Cc, self.negative_slope, self.concat, res, self.bias, False,
-                                _drop(self))
+                                _drop(self), e_feat)
         return super().forward(x, edge_index, edge_attr, return_attention_weights)
 
 
 class B200TransformerConv(tgnn.TransformerConv):
     def forward(self, x, edge_index, edge_attr=None, return_attention_weights=None):
         xs = _pair(x)
-        if (xs[0].dim() == 2 and xs[1] is not None and _attn_fast(self, xs[0], xs[1]) and edge_attr is None
-                and self.lin_edge is None and return_attention_weights is None and isinstance(edge_index, Tensor)
-                and edge_index.layout == torch.strided):
+        if (xs[0].dim() == 2 and xs[1] is not None and _attn_fast(self, xs[0], xs[1], edge_attr)
+                and (edge_attr is None) == (self.lin_edge is None) and return_attention_weights is None
+                and isinstance(edge_index, Tensor) and edge_index.layout == torch.strided):
             H, Cc = self.heads, self.out_channels
             query = dense.linear(xs[1], self.lin_query.weight, self.lin_query.bias)
             w_kv = torch.cat([self.lin_key.weight, self.lin_value.weight], dim=0)
@@ -238,7 +245,10 @@ class B200TransformerConv(tgnn.TransformerConv):
             g = _graph(edge_index, xs[0].size(0), xs[1].size(0), self.flow)
             x_skip = dense.linear(xs[1], self.lin_skip.weight, self.lin_skip.bias) if self.root_weight else None
             w_beta = self.lin_beta.weight if self.lin_beta is not None else None
-            return C.transformer_conv(query, kv, g, H, Cc, self.concat, x_skip, w_beta, False, _drop(self))
+            e_feat = None
+            if edge_attr is not None:                                           # transformer_conv.py:258-261
+                e_feat = dense.linear(edge_attr.view(-1, 1) if edge_attr.dim() == 1 else edge_attr, self.lin_edge.weight)
+            return C.transformer_conv(query, kv, g, H, Cc, self.concat, x_skip, w_beta, False, _drop(self), e_feat)
         return super().forward(x, edge_index, edge_attr, return_attention_weights)
 
 

@@ -24,17 +24,19 @@ DEV = "cuda"
 
 
 def ref_attention(mode, src, dst, n_dst, H, C, v, k=None, q=None, s_src=None, s_dst=None, att=None, s_edge=None,
-                  slope=0.2, scale=1.0, keep=None):
+                  slope=0.2, scale=1.0, keep=None, e_feat=None):
     vj = v[src].view(-1, H, C)
+    ef = 0.0 if e_feat is None else e_feat.view(-1, H, C)          # lin_edge(edge_attr) of the edge_dim layers
     if mode == "gat":
         pre = s_src[src] + s_dst[dst]
         if s_edge is not None:
             pre = pre + s_edge
         s = F.leaky_relu(pre, slope)
     elif mode == "gatv2":
-        s = (F.leaky_relu(vj + q[dst].view(-1, H, C), slope) * att.view(1, H, C)).sum(-1)
+        s = (F.leaky_relu(vj + q[dst].view(-1, H, C) + ef, slope) * att.view(1, H, C)).sum(-1)      # gatv2_conv.py:358-362
     else:
-        s = (q[dst].view(-1, H, C) * k[src].view(-1, H, C)).sum(-1) * scale
+        s = (q[dst].view(-1, H, C) * (k[src].view(-1, H, C) + ef)).sum(-1) * scale                    # transformer_conv.py:258-263
+        vj = vj + ef                                                                                # transformer_conv.py:270-272
     idx = dst.view(-1, 1).expand(-1, H)
     smax = torch.full((n_dst, H), -math.inf, dtype=s.dtype, device=s.device).scatter_reduce(0, idx, s.detach(), "amax")
     ex = (s - smax[dst]).exp()
@@ -284,3 +286,44 @@ def test_attention_layers_train_with_dropout():
             mean = torch.stack([a(x, g) for _ in range(100)]).mean(0)
             ref = b(x, ei)
         assert float((mean - ref).abs().mean() / ref.abs().mean()) < 0.1, cls.__name__
+
+
+@pytest.mark.parametrize("chunk", [512, 16])
+@pytest.mark.parametrize("mode,H,C,dtype", [("gatv2", 8, 16, torch.float32), ("gatv2", 8, 16, torch.bfloat16), ("gatv2", 2, 128, torch.float32),
+                                            ("gatv2", 3, 4, torch.float32), ("dot", 8, 16, torch.float32), ("dot", 4, 32, torch.bfloat16),
+                                            ("dot", 2, 128, torch.float32), ("dot", 1, 4, torch.float32)])
+def test_attention_with_per_edge_feature_rows(mode, H, C, dtype, chunk):
+    """`edge_dim`: lin_edge(edge_attr) [E, H*C] inside GATv2's leaky_relu (gatv2_conv.py:358-360) / added to the key and the
+    value of TransformerConv (transformer_conv.py:258-272) -- forward, returned coefficients, and every gradient incl. the
+    per-edge one, vs the unfused fp64 formula; with dropout on top for one case per mode."""
+    p = _problem(mode, H, C, dtype, seed=H * 7 + C + 3 * len(mode))
+    n_src, n_dst, E = p["v"].size(0), p["gout"].size(0), p["src"].numel()
+    p["e_feat"] = (torch.randn(E, H * C, generator=torch.Generator().manual_seed(C)) * 0.7).to(dtype).double()
+    names = [n for n in ("v", "k", "q", "att", "e_feat") if n in p]
+    scale = 1.0 / math.sqrt(C)
+    graph = CSRGraph(p["src"].to(DEV), p["dst"].to(DEV), n_src, n_dst, chunk=chunk)
+    perm = graph.perm.long()
+    feat = ("v", "k", "q", "e_feat")
+    ours = {n: (p[n].to(dtype) if n in feat else p[n].float()).to(DEV).requires_grad_() for n in names}
+    pd = 0.3 if (H, C) == (8, 16) and dtype == torch.float32 else 0.0
+    out, alpha = Fn.attention(mode, graph, H, C, negative_slope=0.2, scale=scale, return_alpha=True, dropout_p=pd, dropout_seed=5,
+                              **ours)
+    out.backward(p["gout"].to(dtype).to(DEV))
+    keep = None
+    if pd > 0:
+        keep = torch.empty_like(alpha, dtype=torch.float64)
+        keep[perm] = (alpha != 0).double() / (1 - pd)
+    ref_in = {n: p[n].clone().to(DEV).requires_grad_() for n in names}
+    ref_out, ref_alpha = ref_attention(mode, p["src"].to(DEV), p["dst"].to(DEV), n_dst, H, C, slope=0.2, scale=scale, keep=keep, **ref_in)
+    ref_out.backward(p["gout"].to(DEV))
+    fp32 = dtype == torch.float32
+
+    def close(a, b, what, t):
+        a, b = a.detach().double(), b.detach().double()
+        err = (a - b).abs().max().item()
+        assert err <= t * max(b.abs().max().item(), 1e-3), f"{what}: max err {err:.3e} (scale {b.abs().max().item():.3e})"
+
+    close(out, ref_out, "out", 2e-5 if fp32 else 1.5e-2)
+    close(alpha, ref_alpha[perm], "alpha", 1e-4 if fp32 else 1.5e-2)
+    for n in names:
+        close(ours[n].grad, ref_in[n].grad, "grad_" + n, 2e-4 if fp32 else 3e-2)

@@ -209,7 +209,11 @@ CASES = [("GCNConv", (32, 16), {}), ("GCNConv", (32, 16), {"normalize": False, "
          ("SAGEConv", (32, 16), {"project": True, "normalize": True}), ("GraphConv", (32, 16), {"aggr": "max"}),
          ("GATConv", (32, 8), {"heads": 4}), ("GATConv", (32, 8), {"heads": 2, "concat": False, "residual": True, "edge_dim": 3}),
          ("GATv2Conv", (32, 8), {"heads": 4}), ("GATv2Conv", (32, 6), {"heads": 3, "share_weights": True, "residual": True}),
+         ("GATv2Conv", (32, 8), {"heads": 4, "edge_dim": 3}),
+         ("GATv2Conv", (32, 8), {"heads": 2, "edge_dim": 3, "add_self_loops": False, "concat": False, "fill_value": 0.5}),
          ("TransformerConv", (32, 8), {"heads": 4}), ("TransformerConv", (32, 8), {"heads": 2, "concat": False, "beta": True}),
+         ("TransformerConv", (32, 8), {"heads": 4, "edge_dim": 3}),
+         ("TransformerConv", (32, 16), {"heads": 2, "edge_dim": 3, "concat": False, "beta": True}),
          ("RGCNConv", (32, 16, 3), {}), ("RGCNConv", (32, 16, 3), {"num_bases": 2, "aggr": "sum"}),
          ("RGCNConv", (32, 16, 3), {"num_blocks": 4}), ("FastRGCNConv", (32, 16, 3), {})]
 
