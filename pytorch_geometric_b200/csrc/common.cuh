@@ -62,8 +62,6 @@ __device__ __forceinline__ Vec16 ldg_row16(const void* p) {
                  : "l"(p));
     return v;
 }
-// L2 prefetch of a line another pass of the same thread will read (no register, no scoreboard entry).
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Streaming 128-bit load (data read exactly once: evict first).
 __device__ __forceinline__ Vec16 ldg_stream16(const void* p) {
     Vec16 v;

@@ -210,9 +210,6 @@ multi_aggr_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, const
                     const int64_t c = GATHER ? static_cast<int64_t>(ldg_idx(col + e + u)) : (e + u);
                     buf[u] = GATHER ? ldg_row16(xb + static_cast<size_t>(c) * row_bytes + voff)
                                     : ldg_stream16(xb + static_cast<size_t>(c) * row_bytes + voff);
-                    // rows wider than the lane group: the next vector pass re-walks the same source rows -- send their
-                    // next G * 16 bytes towards L2 while this pass waits on DRAM anyway
-                    if (GATHER && v + G < n_vec) prefetch_l2(xb + static_cast<size_t>(c) * row_bytes + voff + G * 16);
                 }
             }
 #pragma unroll
@@ -277,13 +274,7 @@ multi_aggr_masked_kernel(const I* __restrict__ rowptr, const I* __restrict__ col
             Vec16 buf[UNR];
 #pragma unroll
             for (int u = 0; u < UNR; ++u)
-                if (e + u < end) {
-                    const char* rp = xb + static_cast<size_t>(ldg_idx(col + e + u)) * row_bytes + voff;
-                    buf[u] = ldg_row16(rp);
-                    // the second vector pass (v + 32) reads the other half of the same source row: start it towards L2 now,
-                    // so that pass pays an L2 hit instead of a second DRAM round trip per edge
-                    if (v + 32 < n_vec) prefetch_l2(rp + 512);
-                }
+                if (e + u < end) buf[u] = ldg_row16(xb + static_cast<size_t>(ldg_idx(col + e + u)) * row_bytes + voff);
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 if (e + u < end) {
