@@ -142,12 +142,51 @@ class _ScatterCOO(torch.autograd.Function):
             ties = ops.scatter_coo(eq, index, ctx.dim_size, "sum") + (o2 == 0).to(torch.float32)
             g = eq * ops.gather_rows(g2 / ties, index)
         else:
-            raise NotImplementedError("backward of scatter(reduce='mul') is not implemented")
+            # ATen's scatter_reduce_('prod') rule (FunctionsManual.cpp, scatter_reduce_backward; `self` is all ones here):
+            # a value that is the ONLY zero of its group gets grad * (product of the others), every other value gets
+            # grad * result / value (0 when its group holds a zero elsewhere, 0 for every member of a group with >= 2 zeros)
+            s2, o2 = src.view(src.size(0), -1).float(), out.view(out.size(0), -1).float()
+            zero = s2 == 0
+            n_zero = ops.gather_rows(ops.scatter_coo(zero.to(torch.float32), index, ctx.dim_size, "sum"), index)
+            single = zero & (n_zero == 1)
+            others = ops.scatter_coo(torch.where(single, torch.ones_like(s2), s2), index, ctx.dim_size, "mul")
+            g = torch.where(single, ops.gather_rows(g2 * others, index), ops.gather_rows(g2 * o2, index) / torch.where(zero, torch.ones_like(s2), s2))
         return g.view((index.numel(), ) + tuple(grad_out.shape[1:])), None, None, None
 
 
 def scatter_coo(src: Tensor, index: Tensor, dim_size: int, reduce: str = "sum") -> Tensor:
     return _ScatterCOO.apply(src, index, dim_size, reduce)
+
+
+class _ScatterAny(torch.autograd.Function):
+    """scatter(reduce='any') (utils/_scatter.py:75-77: `src.new_zeros(size).scatter_(dim, index, src)`): one member of
+    every group.  Which one is unspecified on CUDA; here it is the LAST one in index order -- what the reference's CPU
+    kernel produces -- found by an integer amax over the positions, then one row gather.  Backward = scatter_'s:
+    every member receives its group's gradient."""
+
+    @staticmethod
+    def forward(ctx, src: Tensor, index: Tensor, dim_size: int):
+        pos = torch.arange(index.numel(), device=index.device, dtype=torch.int64)
+        last = torch.full((dim_size, ), -1, dtype=torch.int64, device=index.device).scatter_reduce_(
+            0, index.long(), pos, "amax", include_self=True)
+        s2 = src.contiguous().view(src.size(0), -1)
+        if s2.size(0) == 0:
+            out = s2.new_zeros((dim_size, s2.size(1)))
+        else:
+            out = ops.gather_rows(s2, ops.convert_index(last.clamp(min=0), index.dtype))
+            out = out * (last >= 0).to(out.dtype).view(-1, 1)                    # empty groups stay 0
+        ctx.save_for_backward(index)
+        return out.view((dim_size, ) + tuple(src.shape[1:]))
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        index, = ctx.saved_tensors
+        g = ops.gather_rows(grad_out.contiguous().view(grad_out.size(0), -1), index)
+        return g.view((index.numel(), ) + tuple(grad_out.shape[1:])), None, None
+
+
+def scatter_any(src: Tensor, index: Tensor, dim_size: int) -> Tensor:
+    return _ScatterAny.apply(src, index, dim_size)
 
 
 class _SoftmaxCSR(torch.autograd.Function):

@@ -2,8 +2,7 @@
 
 Every routed function keeps the reference's signature, validation and error messages.  Routing rule: the engine takes
 a call iff the feature tensor is a CUDA tensor of dtype float32 / bfloat16 and the reduction is one it implements with
-the reference's semantics; everything else -- CPU tensors, float64 / half / integer data, reduce='any', the backward of
-reduce='mul' -- falls through to the UNTOUCHED reference function (`__wrapped__`), which is also how the parity oracle
+the reference's semantics; everything else -- CPU tensors, float64 / half / integer data, reduce='any' (whose CUDA result is unspecified in the reference itself) -- falls through to the UNTOUCHED reference function (`__wrapped__`), which is also how the parity oracle
 keeps working next to the engine.  Nothing is ever silently computed on the CPU by the engine.
 """
 from __future__ import annotations
@@ -86,7 +85,7 @@ def make_scatter(theirs):
                     return out
             src = src.materialise()
         r = _REDUCE.get(reduce)
-        if (not engine_ok(src) or _compiling() or r is None or (r == "mul" and src.requires_grad)
+        if (not engine_ok(src) or _compiling() or r is None
                 or not isinstance(index, Tensor) or index.dim() != 1):
             return theirs(src, index, dim, dim_size, reduce)           # incl. every argument error of the reference
         d = src.dim() + dim if dim < 0 else dim

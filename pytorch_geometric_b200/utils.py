@@ -37,12 +37,13 @@ def scatter(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[int] = 
         raise ValueError(f"The `dim` argument must lay between 0 and {src.dim() - 1} (got {dim})")
     if reduce not in ("sum", "add", "mean", "min", "max", "amin", "amax", "mul", "any"):
         raise ValueError(f"Encountered invalid `reduce` argument '{reduce}'")
-    if reduce == "any":
-        raise NotImplementedError("scatter(reduce='any') is not on the aggregation path")
     reduce = {"add": "sum", "amin": "min", "amax": "max"}.get(reduce, reduce)
     if dim_size is None:
         dim_size = (ops.index_stats(index)[1] + 1) if index.numel() > 0 else 0
     x, moved = _move_dim0(src, dim)
+    if reduce == "any":
+        out = Fn.scatter_any(x if x.dtype in (torch.float32, torch.bfloat16) else x.float(), index, dim_size).to(x.dtype)
+        return out.movedim(0, dim) if moved else out
     if sorted and reduce != "mul" and x.dtype in (torch.float32, torch.bfloat16):
         out = Fn.segment(x, ops.index2ptr(index, dim_size), reduce)
     else:

@@ -282,6 +282,42 @@ def test_scatter_coo_and_sorted_vs_oracle(feat, red):
         U.scatter(cu(src), cu(index), 0, N, "std")
 
 
+def test_scatter_mul_backward_and_any_follow_the_aten_rules():
+    """The two reduce modes that used to be gaps: `mul` = new_ones().scatter_reduce_('prod', include_self=True) with ATen's
+    zero-aware backward, `any` = new_zeros().scatter_() (utils/_scatter.py:75-77,130-135).  Reference = those ATen calls on
+    the CPU (where `any` deterministically keeps the last member in index order)."""
+    rng = np.random.default_rng(4)
+    N, E, F = 60, 900, 5
+    index = torch.from_numpy(rng.integers(0, N - 4, size=E))
+    src = torch.from_numpy((1.0 + 0.3 * rng.standard_normal((E, F))).astype(np.float32))
+    src[rng.random((E, F)) < 0.02] = 0.0                                   # groups with one zero, a few with several
+    src[index == 7] = src[index == 7].abs() + 0.1
+    src[torch.nonzero(index == 7)[0], 2] = 0.0                            # exactly one zero in group 7, feature 2
+    gout = torch.from_numpy(rng.standard_normal((N, F)).astype(np.float32))
+    # ---- mul
+    a = src.clone().requires_grad_()
+    want = a.new_ones(N, F).scatter_reduce_(0, index.view(-1, 1).expand(-1, F), a, "prod", include_self=True)
+    want.backward(gout)
+    b = src.clone().to(DEV).requires_grad_()
+    got = U.scatter(b, index.to(DEV), 0, N, "mul")
+    got.backward(gout.to(DEV))
+    assert_close(npy(got), want.detach().numpy(), rtol=2e-5, atol=1e-6)
+    scale = float(a.grad.abs().max())
+    assert_close(npy(b.grad), a.grad.numpy(), rtol=1e-4, atol=1e-5 * scale)
+    assert (npy(b.grad)[a.grad.numpy() == 0] == 0).all()                   # groups with >= 2 zeros: exactly zero
+    # ---- any
+    a = src.clone().requires_grad_()
+    want = a.new_zeros(N, F).scatter_(0, index.view(-1, 1).expand(-1, F), a)
+    want.backward(gout)
+    b = src.clone().to(DEV).requires_grad_()
+    got = U.scatter(b, index.to(DEV), 0, N, "any")
+    got.backward(gout.to(DEV))
+    assert np.array_equal(npy(got), want.detach().numpy())
+    assert np.array_equal(npy(b.grad), a.grad.numpy())
+    got_t = U.scatter(src.T.contiguous().to(DEV), index.to(DEV), 1, N, "any")        # dim != 0
+    assert np.array_equal(npy(got_t).T, want.detach().numpy())
+
+
 @pytest.mark.parametrize("red", ["sum", "mean", "min", "max"])
 def test_segment_golden_and_dense(red):
     g = load_golden("segment")
