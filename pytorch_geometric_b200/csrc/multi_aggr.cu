@@ -599,9 +599,9 @@ int multi_prep_typed(const void* rowptr, MultiPrep p, int64_t n_rows, int64_t fe
     return B200MP_OK;
 }
 
-// fp32 vector form of the backward: a lane group per item, 16-byte loads of the (four + two conditional)
-// per-destination rows, two destinations in flight.
-template <typename I, int G, bool SEGMENT>
+// fp32 vector form of the gather-mode backward (rows the masked warp-per-row kernel does not take): a lane group per source
+// row, 16-byte loads of the (four + two conditional) per-destination rows, two destinations in flight.
+template <typename I, int G>
 __global__ void __launch_bounds__(128, 6)
 multi_aggr_backward_vec_kernel(const I* __restrict__ ptr, const I* __restrict__ idx, const float* __restrict__ x,
                                MultiGrad g, float* __restrict__ grad_x, int64_t n_items, int n_vec) {
@@ -610,8 +610,8 @@ multi_aggr_backward_vec_kernel(const I* __restrict__ ptr, const I* __restrict__ 
     const int64_t j = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
     if (j >= n_items) return;
     const size_t row_bytes = static_cast<size_t>(n_vec) * 16;
-    const int64_t begin = SEGMENT ? j : static_cast<int64_t>(ptr[j]);
-    const int64_t end = SEGMENT ? j + 1 : static_cast<int64_t>(ptr[j + 1]);
+    const int64_t begin = static_cast<int64_t>(ptr[j]);
+    const int64_t end = static_cast<int64_t>(ptr[j + 1]);
     for (int v = lig; v < n_vec; v += G) {
         const size_t voff = static_cast<size_t>(v) * 16;
         float xv[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -652,7 +652,7 @@ multi_aggr_backward_vec_kernel(const I* __restrict__ ptr, const I* __restrict__ 
                         if (g.b) t = fmaf(xv[i], __uint_as_float(b[u][1].w[i]), t);
                         if (hit_mn && xv[i] == __uint_as_float(b[u][2].w[i])) t += __uint_as_float(gmn.w[i]);
                         if (hit_mx && xv[i] == __uint_as_float(b[u][3].w[i])) t += __uint_as_float(gmx.w[i]);
-                        acc[i] = SEGMENT ? t : __fadd_rn(acc[i], t);
+                        acc[i] = __fadd_rn(acc[i], t);
                     }
                 }
             }
@@ -666,14 +666,15 @@ multi_aggr_backward_vec_kernel(const I* __restrict__ ptr, const I* __restrict__ 
 // attention.cu): the edge loop no longer alternates "index -> rows -> conditional rows" round trips, the next two
 // destinations' rows are already in flight while the tie-gradient rows of the current two are fetched.  Destination
 // indices are read 32 at a time (one coalesced load per lane) and broadcast with shuffles.
-// MASK: the forward's hit bits (one byte per edge and vector, CSR edge order, addressed through t2csr) replace the two
-// 16-byte min / max vectors of the destination: 2 rows + 1 byte per edge instead of 4 rows, plus the tie-gradient
-// vectors of the lanes that hit (on a degree-d destination every edge attains the extremum of ~1/d of the features).
-template <typename I, int VPL, bool MASK, int kMbT>
+// The forward's hit bits (one byte per edge and vector, CSR edge order, addressed through t2csr) replace the two 16-byte
+// min / max vectors of the destination: 2 rows + 1 byte per edge instead of 4 rows, plus the tie-gradient vectors of the
+// lanes that hit (on a degree-d destination every edge attains the extremum of ~1/d of the features).  (A variant of this
+// kernel that staged all four rows instead of using the bits was slower than the register form: 113 vs 73 ms.)
+template <typename I, int VPL, int kMbT>
 __global__ void __launch_bounds__(kMbT, kMbT == 32 ? 20 : 5)
 multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict__ idx, const float* __restrict__ x,
                                   MultiGrad g, float* __restrict__ grad_x, int64_t n_items, int n_vec) {
-    constexpr int D = 2, UNR = 2, NR = MASK ? 2 : 4;
+    constexpr int D = 2, UNR = 2, NR = 2;                  // staged rows: additive term, multiplier of x
     extern __shared__ __align__(16) unsigned char mb_stage[];
     const int lane = threadIdx.x & 31;
     const int64_t j = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -697,8 +698,7 @@ multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict
     auto slot = [&](int d, int u, int r, int k) {
         return base + static_cast<size_t>(((d * UNR + u) * NR + r) * VPL + k) * (kMbT * 16);
     };
-    const char* rows[4] = {reinterpret_cast<const char*>(g.a), reinterpret_cast<const char*>(g.b),
-                           static_cast<const char*>(g.mn), static_cast<const char*>(g.mx)};
+    const char* rows[NR] = {reinterpret_cast<const char*>(g.a), reinterpret_cast<const char*>(g.b)};
     const I* t2csr = static_cast<const I*>(g.t2csr);
     const bool use_mn = g.gmin != nullptr, use_mx = g.gmax != nullptr;
     I i0 = 0, i1 = 0, p0 = 0, p1 = 0;
@@ -707,7 +707,7 @@ multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict
         ireg = preg = 0;
         if (b * 32 + lane < deg) {
             ireg = ldg_idx(idx + begin + b * 32 + lane);
-            if (MASK) preg = ldg_idx(t2csr + begin + b * 32 + lane);
+            preg = ldg_idx(t2csr + begin + b * 32 + lane);
         }
     };
     load_batch(0, i0, p0);
@@ -722,8 +722,7 @@ multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict
         for (int u = 0; u < UNR; ++u) {
             const int e = t * UNR + u;
             const size_t off = static_cast<size_t>(__shfl_sync(0xffffffffu, ireg, e & 31)) * row_bytes;
-            size_t moff = 0;
-            if (MASK) moff = static_cast<size_t>(__shfl_sync(0xffffffffu, preg, e & 31)) * n_vec;
+            const size_t moff = static_cast<size_t>(__shfl_sync(0xffffffffu, preg, e & 31)) * n_vec;
             off_nxt[u] = off;
             if (e < deg) {
 #pragma unroll
@@ -733,7 +732,7 @@ multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict
 #pragma unroll
                     for (int r = 0; r < NR; ++r)
                         if (rows[r]) cp_async16(slot(d, u, r, k), rows[r] + o);
-                    if (MASK) m_nxt[u][k] = __ldg(g.hit_mask + moff + lane + k * 32);
+                    m_nxt[u][k] = __ldg(g.hit_mask + moff + lane + k * 32);
                 }
             }
         }
@@ -770,20 +769,7 @@ multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict
             for (int k = 0; k < VPL; ++k) {
                 hits[u][k] = 0;
                 if (t * UNR + u >= deg || !valid[k]) continue;
-                if (MASK) {
-                    hits[u][k] = m_cur[u][k] & ((use_mn ? 0x0fu : 0u) | (use_mx ? 0xf0u : 0u));
-                } else {
-                    if (g.mn) {
-                        const Vec16 m = *reinterpret_cast<const Vec16*>(slot(d, u, 2, k));
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) hits[u][k] |= xv[k][i] == __uint_as_float(m.w[i]) ? 1u << i : 0u;
-                    }
-                    if (g.mx) {
-                        const Vec16 m = *reinterpret_cast<const Vec16*>(slot(d, u, 3, k));
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) hits[u][k] |= xv[k][i] == __uint_as_float(m.w[i]) ? 16u << i : 0u;
-                    }
-                }
+                hits[u][k] = m_cur[u][k] & ((use_mn ? 0x0fu : 0u) | (use_mx ? 0xf0u : 0u));
                 const size_t o = off_cur[u] + static_cast<size_t>(lane + k * 32) * 16;
                 if (hits[u][k] & 0x0fu) gmn[u][k] = ldg_row16(reinterpret_cast<const char*>(g.gmin) + o);
                 if (hits[u][k] & 0xf0u) gmx[u][k] = ldg_row16(reinterpret_cast<const char*>(g.gmax) + o);
@@ -828,18 +814,18 @@ multi_aggr_backward_staged_kernel(const I* __restrict__ ptr, const I* __restrict
                          ElemTraits<float>::pack(acc[k]));
 }
 
-template <typename I, int VPL, bool MASK, int kMbT>
+template <typename I, int VPL, int kMbT>
 int multi_bwd_staged_launch(const I* ptr, const I* idx, const float* x, const MultiGrad& g, float* grad_x, int64_t n_items,
                             int n_vec, cudaStream_t stream) {
-    // 2 stages x 2 destinations x (2 | 4) rows x VPL vectors of 16 bytes per thread
-    const size_t smem = static_cast<size_t>(2) * 2 * (MASK ? 2 : 4) * VPL * kMbT * 16;
+    // 2 stages x 2 destinations x 2 rows x VPL vectors of 16 bytes per thread
+    const size_t smem = static_cast<size_t>(2) * 2 * 2 * VPL * kMbT * 16;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-        B200MP_CUDA(cudaFuncSetAttribute(multi_aggr_backward_staged_kernel<I, VPL, MASK, kMbT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B200MP_CUDA(cudaFuncSetAttribute(multi_aggr_backward_staged_kernel<I, VPL, kMbT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
         attr_set = true;
     }
-    multi_aggr_backward_staged_kernel<I, VPL, MASK, kMbT><<<static_cast<unsigned>(ceil_div(n_items, kMbT / 32)), kMbT, smem, stream>>>(
+    multi_aggr_backward_staged_kernel<I, VPL, kMbT><<<static_cast<unsigned>(ceil_div(n_items, kMbT / 32)), kMbT, smem, stream>>>(
         ptr, idx, x, g, grad_x, n_items, n_vec);
     B200MP_LAUNCH_CHECK();
     return B200MP_OK;
@@ -927,11 +913,11 @@ int multi_typed(const void* rowptr, const void* col, const void* x, MultiOut out
                                      static_cast<const T*>(x), outs, n_rows, feat, plan, stream);
 }
 
-template <typename I, bool SEGMENT>
+template <typename I>
 void multi_bwd_vec_launch(const I* ptr, const I* idx, const float* x, const MultiGrad& g, float* grad_x,
                           int64_t n_items, int n_vec, cudaStream_t stream) {
 #define B200MP_MB(G_)                                                                                        \
-    multi_aggr_backward_vec_kernel<I, G_, SEGMENT><<<static_cast<unsigned>(ceil_div(n_items, 128 / G_)), 128, 0, stream>>>( \
+    multi_aggr_backward_vec_kernel<I, G_><<<static_cast<unsigned>(ceil_div(n_items, 128 / G_)), 128, 0, stream>>>( \
         ptr, idx, x, g, grad_x, n_items, n_vec)
     if (n_vec <= 1) B200MP_MB(1);
     else if (n_vec <= 2) B200MP_MB(2);
@@ -1037,12 +1023,12 @@ int multi_bwd_typed(const void* ptr, const void* idx, const void* x, MultiGrad g
             float* gx = static_cast<float*>(grad_x);
             // one-warp CTAs (multi_tune 6, default): no warp waits for the longest of four rows
             if (get_option_multi_tune() == 5)
-                return n_vec > 32 ? multi_bwd_staged_launch<I, 2, true, 128>(p, ix, xf, g, gx, n_items, n_vec, stream)
-                                  : multi_bwd_staged_launch<I, 1, true, 128>(p, ix, xf, g, gx, n_items, n_vec, stream);
-            return n_vec > 32 ? multi_bwd_staged_launch<I, 2, true, 32>(p, ix, xf, g, gx, n_items, n_vec, stream)
-                              : multi_bwd_staged_launch<I, 1, true, 32>(p, ix, xf, g, gx, n_items, n_vec, stream);
+                return n_vec > 32 ? multi_bwd_staged_launch<I, 2, 128>(p, ix, xf, g, gx, n_items, n_vec, stream)
+                                  : multi_bwd_staged_launch<I, 1, 128>(p, ix, xf, g, gx, n_items, n_vec, stream);
+            return n_vec > 32 ? multi_bwd_staged_launch<I, 2, 32>(p, ix, xf, g, gx, n_items, n_vec, stream)
+                              : multi_bwd_staged_launch<I, 1, 32>(p, ix, xf, g, gx, n_items, n_vec, stream);
         } else
-            multi_bwd_vec_launch<I, false>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
+            multi_bwd_vec_launch<I>(static_cast<const I*>(ptr), static_cast<const I*>(idx),
                                            static_cast<const float*>(x), g, static_cast<float*>(grad_x), n_items, n_vec, stream);
         B200MP_LAUNCH_CHECK();
         return B200MP_OK;
