@@ -19,11 +19,17 @@
 // (col == nullptr: x is the materialised [E, F] message matrix, sorted by destination).
 // Hub rows use the same LongRowPlan as the SpMM; their partial state is six fp32 planes per chunk.
 //
-// Backward (both modes) is one kernel as well: with per-destination fp32 rows
+// Backward: an elementwise prologue folds the output gradients into per-destination fp32 rows
 //     A  = g_sum + g_mean/cnt - 2 * g_var' * mean / cnt,   B = 2 * g_var' / cnt,
 //     Gmin = g_min / ties_min,  Gmax = g_max / ties_max          (g_var' = g_var + g_std / (2 std))
-// the gradient of one message value x is  A + x * B + [x == mn] * Gmin + [x == mx] * Gmax, summed over
-// the destinations the value was sent to (one in segment mode, the out-neighbours in gather mode).
+// and the gradient of one message value x is  A + x * B + [x == mn] * Gmin + [x == mx] * Gmax, summed over
+// the destinations the value was sent to (one in segment mode, the out-neighbours in gather mode).  Kernels:
+//   multi_aggr_backward_staged_kernel   gather mode, fp32, 64 < F <= 256: warp per source row, A / B rows staged by
+//                                       cp.async, the [x == mn] / [x == mx] tests read from the forward's hit bits
+//   multi_aggr_backward_vec_kernel      gather mode, other vector shapes: 4 rows + 2 conditional rows per edge
+//   multi_aggr_backward_segment_kernel  segment mode: runs of 8 consecutive messages per lane group
+//   multi_aggr_backward_kernel          scalar fallback (odd widths, bf16)
+// Training forward with hit bits: multi_aggr_masked_kernel (+ multi_aggr_mask_chunks_kernel for hub rows).
 #include "csr_reduce.cuh"
 
 namespace b200mp {
