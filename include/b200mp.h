@@ -52,8 +52,12 @@ enum {
 const char* b200mp_version(void);
 const char* b200mp_last_error(void);          /* thread-local, human readable */
 int b200mp_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
-/* Runtime switches for measurements.  "spmm_impl": 0 = auto (default), 1 = lane-group-per-row
- * kernel only, 2 = persistent TMA-fed kernel wherever it is legal. */
+/* Runtime switches for measurements (A/B of kernel variants; the defaults are the measured best).
+ *   "spmm_impl"    0 = auto (default), 1 = lane-group-per-row kernel only, 2 = persistent TMA-fed kernel wherever legal
+ *   "attn_staged"  2 = cp.async-staged attention sweeps with one-warp CTAs (default), 1 = 4-warp CTAs, 0 = register form;
+ *                  0 also turns the multi-aggregation hit-bit path off
+ *   "multi_tune"   6 = one-warp CTAs for the multi-aggregation row sweeps (default), 5 = 128-thread CTAs
+ *   "gemm_*", "spmm_tune"   tuning knobs of the GEMM / gather kernels (see csrc/core.cu) */
 int b200mp_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------ graph structure (integer work, bit-exact)

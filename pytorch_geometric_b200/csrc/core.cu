@@ -56,7 +56,7 @@ static int g_spmm_tune = 0;
 int get_option_spmm_tune() { return g_spmm_tune; }
 static int g_attn_staged = 2;   // cp.async-staged attention sweeps (csrc/attention.cu): 2 = with one-warp CTAs, 1 = 4-warp CTAs, 0 = register-staged loop
 int get_option_attn_staged() { return g_attn_staged; }
-static int g_multi_tune = 6;    // resident CTAs per SM the masked multi-aggregation sweep is compiled for (5 | 6), multi_aggr.cu
+static int g_multi_tune = 6;    // multi_aggr.cu: 6 = one-warp CTAs for the row sweeps (default), 5 = the 128-thread form, kept for A/B
 int get_option_multi_tune() { return g_multi_tune; }
 
 // Work counters of the persistent kernels: a small device-resident pool, one slot per launch in

@@ -34,8 +34,8 @@
 
 namespace b200mp {
 
-int get_option_attn_staged();   // core.cu: cp.async-staged gathers (default 1)
-int get_option_multi_tune();    // core.cu: resident CTAs per SM of the masked sweep (5 | 6)
+int get_option_attn_staged();   // core.cu: cp.async-staged gathers on (default) / off; also gates the hit-bit path
+int get_option_multi_tune();    // core.cu: 6 (default) = one-warp CTAs for the row sweeps, 5 = the 128-thread form (A/B)
 
 enum { MA_SUM = 0, MA_MEAN, MA_MIN, MA_MAX, MA_VAR, MA_STD, MA_TIES_MIN, MA_TIES_MAX, MA_SLOTS };
 
