@@ -54,6 +54,55 @@ def scatter(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[int] = 
     return out.movedim(0, dim) if moved else out
 
 
+def scatter_argmax(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[int] = None) -> Tensor:
+    """Mirror of torch_geometric.utils.scatter_argmax (utils/_scatter.py:145-182) for the 1-D case it implements: the position
+    of a maximal member of every group; empty groups give dim_size - 1 (the reference's fill value).  The maximum comes from
+    the atomic COO kernel, the position from b200mp_scatter_arg (the smallest tied position; the reference leaves ties to
+    the order of a duplicate-index assignment)."""
+    assert src.dim() == 1 and index.dim() == 1
+    assert dim == 0 or dim == -1
+    assert src.numel() == index.numel()
+    if dim_size is None:
+        dim_size = (ops.index_stats(index)[1] + 1) if index.numel() > 0 else 0
+    x = src.detach().float().view(-1, 1)
+    res = ops.scatter_coo(x, index, dim_size, "max")
+    arg = ops.scatter_arg(x, index, res).view(-1)
+    return torch.where(arg >= src.numel(), arg.new_full((), dim_size - 1), arg).to(index.dtype)
+
+
+def group_argsort(src: Tensor, index: Tensor, dim: int = 0, num_groups: Optional[int] = None, descending: bool = False,
+                  return_consecutive: bool = False, stable: bool = False) -> Tensor:
+    """Mirror of torch_geometric.utils.group_argsort (utils/_scatter.py:185-246): rank of every value inside its group.
+    Index bookkeeping, not a hot path: the value sort is torch's, the group offsets come from the engine's degree / ptr."""
+    assert src.dim() == 1 and index.dim() == 1
+    assert dim == 0 or dim == -1
+    assert src.numel() == index.numel()
+    if src.numel() == 0:
+        return torch.zeros_like(src)
+    src = src - src.min()
+    src = src / src.max()
+    src = src - 2 * index if descending else src + 2 * index
+    perm = src.argsort(descending=descending, stable=stable)
+    out = torch.empty_like(index)
+    out[perm] = torch.arange(index.numel(), device=index.device, dtype=index.dtype)
+    if return_consecutive:
+        return out
+    if num_groups is None:
+        num_groups = ops.index_stats(index)[1] + 1
+    ptr = torch.zeros(num_groups + 1, dtype=index.dtype, device=index.device)
+    ptr[1:] = ops.degree(index, num_groups).to(index.dtype).cumsum(0)
+    return out - ptr[index]
+
+
+def group_cat(tensors, indices, dim: int = 0, return_index: bool = False):
+    """Mirror of torch_geometric.utils.group_cat (utils/_scatter.py:249-300): concatenation grouped by the index tensors
+    (one stable sort of the concatenated indices, one row gather)."""
+    assert len(tensors) == len(indices)
+    index, perm = torch.cat(indices).sort(stable=True)
+    out = torch.cat(tensors, dim=dim).index_select(dim, perm)
+    return (out, index) if return_index else out
+
+
 def segment(src: Tensor, ptr: Tensor, reduce: str = "sum") -> Tensor:
     """Mirror of torch_geometric.utils.segment (utils/_segment.py:11-50); ptr must be 1-D."""
     if ptr.dim() != 1:

@@ -299,3 +299,26 @@ def test_scatter_max_and_spmm_max_return_the_arg(tg, plugin):
         prod = val[b:e, None] * mat[col[b:e]]
         assert torch.equal(arg[r].cpu(), b + prod.argmax(0)) and torch.allclose(out[r].cpu(), prod.max(0).values)
     del order
+
+
+def test_index_bookkeeping_mirrors_match_the_reference(tg):
+    """scatter_argmax / group_argsort / group_cat (utils/_scatter.py:145-300) of the standalone mirror vs the reference's own
+    functions on the CPU (tie-free values: the reference leaves ties to the order of a duplicate-index assignment)."""
+    from pytorch_geometric_b200 import utils as U
+    g = torch.Generator().manual_seed(12)
+    N, E = 70, 900
+    index = torch.randint(0, N - 5, (E, ), generator=g)
+    src = torch.randperm(E, generator=g).float() * 0.37 - 100.0
+    want = tg.utils.scatter_argmax(src, index, dim_size=N)
+    got = U.scatter_argmax(src.to(DEV), index.to(DEV), dim_size=N)
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(U.scatter_argmax(src.to(DEV), index.to(DEV)).cpu(), tg.utils.scatter_argmax(src, index))
+    for kw in ({}, {"descending": True}, {"return_consecutive": True}, {"stable": True, "num_groups": N}):
+        want = tg.utils.group_argsort(src, index, **kw)
+        got = U.group_argsort(src.to(DEV), index.to(DEV), **kw)
+        assert torch.equal(got.cpu(), want), kw
+    x1, x2 = torch.randn(40, 3, generator=g), torch.randn(25, 3, generator=g)
+    i1, i2 = torch.sort(torch.randint(0, 9, (40, ), generator=g))[0], torch.sort(torch.randint(0, 9, (25, ), generator=g))[0]
+    want, wi = tg.utils.group_cat([x1, x2], [i1, i2], return_index=True)
+    got, gi = U.group_cat([x1.to(DEV), x2.to(DEV)], [i1.to(DEV), i2.to(DEV)], return_index=True)
+    assert torch.equal(got.cpu(), want) and torch.equal(gi.cpu(), wi)
