@@ -309,10 +309,11 @@ def test_index_bookkeeping_mirrors_match_the_reference(tg):
     N, E = 70, 900
     index = torch.randint(0, N - 5, (E, ), generator=g)
     src = torch.randperm(E, generator=g).float() * 0.37 - 100.0
-    want = tg.utils.scatter_argmax(src, index, dim_size=N)
+    from torch_geometric.utils._scatter import scatter_argmax as ref_argmax        # (not re-exported by utils/__init__)
+    want = ref_argmax(src, index, dim_size=N)
     got = U.scatter_argmax(src.to(DEV), index.to(DEV), dim_size=N)
     assert torch.equal(got.cpu(), want)
-    assert torch.equal(U.scatter_argmax(src.to(DEV), index.to(DEV)).cpu(), tg.utils.scatter_argmax(src, index))
+    assert torch.equal(U.scatter_argmax(src.to(DEV), index.to(DEV)).cpu(), ref_argmax(src, index))
     for kw in ({}, {"descending": True}, {"return_consecutive": True}, {"stable": True, "num_groups": N}):
         want = tg.utils.group_argsort(src, index, **kw)
         got = U.group_argsort(src.to(DEV), index.to(DEV), **kw)
