@@ -192,6 +192,46 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
             }
             cp_async_wait<1>();
             const int d = t & (D - 1);
+            if constexpr (MODE == ATTN_GAT) {
+                // GAT scores need no feature data: take the stage's UNR logits first, move the running max ONCE and rescale
+                // the accumulators once per stage instead of once per edge (the sweep is issue-bound after the staging:
+                // 77 % of the issue slots busy in profiles/r2_attn_v3.summary.csv)
+                float lg[UNR];
+                float mb = m[0];
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int j = t * PER + u * S + sub;
+                    lg[u] = -__builtin_inff();
+                    if (j < deg && valid[0]) {
+                        float sc = *sslot(d, u);
+                        if (a.s_edge) sc += __ldg(a.s_edge + (begin + j) * a.heads + head[0]);
+                        lg[u] = leaky_f(sc + sd[0], a.slope);
+                        mb = fmaxf(mb, lg[u]);
+                        any = true;
+                    }
+                }
+                if (any) {                                          // (a lane group whose edges are exhausted keeps m = -inf)
+                    const float rs = fexp(m[0] - mb);               // 0 on the first stage (m = -inf)
+                    s[0] *= rs;
+#pragma unroll
+                    for (int i = 0; i < EPV; ++i) acc[0][i] *= rs;
+                    m[0] = mb;
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int j = t * PER + u * S + sub;
+                        if (j < deg) {
+                            float f[EPV];
+                            ElemTraits<T>::unpack(*reinterpret_cast<const Vec16*>(vslot(d, u, 0)), f);
+                            const float p = fexp(lg[u] - mb);
+                            s[0] += p;                              // the softmax denominator ignores dropout
+                            const float pk = p * drop_factor(a, begin + j, head[0]);
+#pragma unroll
+                            for (int i = 0; i < EPV; ++i) acc[0][i] = fmaf(pk, f[i], acc[0][i]);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 const int j = t * PER + u * S + sub;
@@ -229,6 +269,7 @@ attn_fwd_kernel(const I* __restrict__ rowptr, const I* __restrict__ col, AttnArg
                     for (int i = 0; i < EPV; ++i) acc[0][i] = fmaf(acc[0][i], rs, pk * f[i]);
                     m[0] = mn;
                 }
+            }
             }
         }
         cp_async_wait<0>();
