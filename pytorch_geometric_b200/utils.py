@@ -72,35 +72,42 @@ def scatter_argmax(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[
 
 def group_argsort(src: Tensor, index: Tensor, dim: int = 0, num_groups: Optional[int] = None, descending: bool = False,
                   return_consecutive: bool = False, stable: bool = False) -> Tensor:
-    """Mirror of torch_geometric.utils.group_argsort (utils/_scatter.py:185-246): rank of every value inside its group.
-    Index bookkeeping, not a hot path: the value sort is torch's, the group offsets come from the engine's degree / ptr."""
-    assert src.dim() == 1 and index.dim() == 1
-    assert dim == 0 or dim == -1
-    assert src.numel() == index.numel()
-    if src.numel() == 0:
+    """Rank of every value inside its group -- the contract of torch_geometric.utils.group_argsort (utils/_scatter.py:185-246).
+    Two stable sorts: the values (torch's float sort), then the group ids with the engine's stable radix sort
+    (`b200mp_sort_by_key`), which also returns the group offsets -- no value normalisation, so large group ids cannot
+    collide in float arithmetic.  Index bookkeeping, not a hot path."""
+    if src.dim() != 1 or index.dim() != 1 or src.numel() != index.numel() or dim not in (0, -1):
+        raise AssertionError("group_argsort is defined for 1-D `src` / `index` of equal length along dim 0")
+    n = src.numel()
+    if n == 0:
         return torch.zeros_like(src)
-    src = src - src.min()
-    src = src / src.max()
-    src = src - 2 * index if descending else src + 2 * index
-    perm = src.argsort(descending=descending, stable=stable)
-    out = torch.empty_like(index)
-    out[perm] = torch.arange(index.numel(), device=index.device, dtype=index.dtype)
-    if return_consecutive:
-        return out
     if num_groups is None:
         num_groups = ops.index_stats(index)[1] + 1
-    ptr = torch.zeros(num_groups + 1, dtype=index.dtype, device=index.device)
-    ptr[1:] = ops.degree(index, num_groups).to(index.dtype).cumsum(0)
-    return out - ptr[index]
+    by_value = torch.argsort(src, descending=descending, stable=True).to(index.dtype)
+    _, by_group, ptr = ops.sort_by_key(ops.permute(index, by_value), num_groups, want_sorted=False)
+    order = ops.permute(by_value, by_group)                         # order[r] = the element at position r of the grouped order
+    rank = torch.empty_like(index)
+    rank[order.long()] = torch.arange(n, device=index.device, dtype=index.dtype)
+    if return_consecutive:
+        return rank
+    return rank - ptr[index.long()]
 
 
 def group_cat(tensors, indices, dim: int = 0, return_index: bool = False):
-    """Mirror of torch_geometric.utils.group_cat (utils/_scatter.py:249-300): concatenation grouped by the index tensors
-    (one stable sort of the concatenated indices, one row gather)."""
-    assert len(tensors) == len(indices)
-    index, perm = torch.cat(indices).sort(stable=True)
-    out = torch.cat(tensors, dim=dim).index_select(dim, perm)
-    return (out, index) if return_index else out
+    """Concatenation grouped by the index tensors -- the contract of torch_geometric.utils.group_cat
+    (utils/_scatter.py:249-300): one stable radix sort of the concatenated group ids, one row gather."""
+    if len(tensors) != len(indices):
+        raise AssertionError("group_cat needs one index tensor per tensor")
+    index = torch.cat(list(indices))
+    n_groups = (ops.index_stats(index)[1] + 1) if index.numel() else 0
+    sorted_index, perm, _ = ops.sort_by_key(index, n_groups, want_ptr=False)
+    stacked = torch.cat(list(tensors), dim=dim)
+    d = dim + stacked.dim() if dim < 0 else dim
+    if d == 0 and stacked.dtype in (torch.float32, torch.bfloat16):
+        out = ops.gather_rows(stacked, perm)
+    else:
+        out = stacked.index_select(d, perm.long())
+    return (out, sorted_index) if return_index else out
 
 
 def segment(src: Tensor, ptr: Tensor, reduce: str = "sum") -> Tensor:
