@@ -56,12 +56,20 @@ def test_state_dict_layout_matches_reference_layers():
 
 
 def test_state_dict_names_and_shapes_equal_the_reference_layers(tg):
-    """Checkpoints are interchangeable: same keys AND shapes as the reference's five layers (GIN's eps is [1])."""
+    """Checkpoints are interchangeable: same keys AND shapes as the reference's layers, option by option (GIN's eps is [1],
+    `edge_dim` adds `lin_edge` / `att_edge`, `share_weights` registers one module under two names, ...)."""
     import pytorch_geometric_b200.nn as ours
     mlp = lambda: torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16))   # noqa: E731
     cases = [("GCNConv", (8, 16), {}), ("SAGEConv", (8, 16), {}), ("SAGEConv", (8, 16), {"project": True}),
              ("GATConv", (8, 4), {"heads": 3}), ("GATConv", (8, 4), {"heads": 2, "concat": False, "residual": True}),
-             ("RGCNConv", (8, 16, 3), {}), ("GINConv", (mlp(), ), {"train_eps": True}), ("GINConv", (mlp(), ), {})]
+             ("RGCNConv", (8, 16, 3), {}), ("GINConv", (mlp(), ), {"train_eps": True}), ("GINConv", (mlp(), ), {}),
+             ("GATConv", (8, 4), {"heads": 2, "edge_dim": 3}), ("GATConv", ((8, 6), 4), {"heads": 2}),
+             ("GATv2Conv", (8, 4), {"heads": 3, "edge_dim": 5}),
+             ("GATv2Conv", (8, 4), {"heads": 2, "share_weights": True, "residual": True, "concat": False}),
+             ("TransformerConv", (8, 4), {"heads": 3, "edge_dim": 5, "beta": True}),
+             ("TransformerConv", (8, 4), {"heads": 2, "concat": False, "bias": False}),
+             ("GraphConv", (8, 16), {}), ("RGCNConv", (8, 16, 3), {"num_bases": 2}), ("RGCNConv", (8, 16, 3), {"num_blocks": 4}),
+             ("FastRGCNConv", (8, 16, 3), {})]
     for name, args, kw in cases:
         a = getattr(ours, name)(*args, **kw).state_dict()
         b = getattr(tg.nn, name)(*args, **kw).state_dict()
