@@ -69,7 +69,7 @@ def test_state_dict_names_and_shapes_equal_the_reference_layers(tg):
              ("TransformerConv", (8, 4), {"heads": 3, "edge_dim": 5, "beta": True}),
              ("TransformerConv", (8, 4), {"heads": 2, "concat": False, "bias": False}),
              ("GraphConv", (8, 16), {}), ("RGCNConv", (8, 16, 3), {"num_bases": 2}), ("RGCNConv", (8, 16, 3), {"num_blocks": 4}),
-             ("FastRGCNConv", (8, 16, 3), {})]
+             ("FastRGCNConv", (8, 16, 3), {}), ("HeteroLinear", (8, 16, 3), {}), ("HeteroLinear", (8, 16, 3), {"bias": False})]
     for name, args, kw in cases:
         a = getattr(ours, name)(*args, **kw).state_dict()
         b = getattr(tg.nn, name)(*args, **kw).state_dict()
